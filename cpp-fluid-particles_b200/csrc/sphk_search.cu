@@ -1,0 +1,318 @@
+// sphk_search.cu -- context lifetime + neighbour search (cell hash -> stable radix sort -> gather ->
+// cell ranges) + permutation / element-wise utilities.  Replaces SPHSystem::neighborSearch,
+// /root/reference/src/SPHSystem.cu:114-127.
+//
+// Design (B200-first, not a translation of the reference's two Thrust sorts with float3 payloads):
+//   1. k_hash_snapshot : one pass over pos(+vel): bit-exact cell key (MUFU.RCP path), writes
+//                        particle2cell (API, pre-sort order, quirk Q2), the sort key, the identity
+//                        index, and a 16-byte-aligned float4 snapshot of pos / vel.
+//   2. cub::DeviceRadixSort::SortPairs on (key, index), only ceil(log2(ncells+1)) key bits
+//                        -> ONE stable sort of 8-byte pairs instead of two sorts of 16-byte pairs.
+//   3. k_gather        : one gather pass writes the sorted API float3 arrays and the packed float4
+//                        shadows (xyz+mass, vel) the sweep kernels read with single LDG.128s.
+//   4. k_cell_start    : cell_start[c] = lower_bound(sortedKeys, c) -- no atomics, no scan, equals
+//                        fill + countingInCell_CUDA + exclusive_scan (SPHSystem.cu:123-125) exactly.
+// HBM-bound; algorithmic bytes per particle are listed in DESIGN.md.
+#include <cub/device/device_radix_sort.cuh>
+#include <cstdio>
+#include <new>
+#include "sphk_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_hash_snapshot(const float* __restrict__ pos, const float* __restrict__ vel, int n, float cellLength,
+                int3 cs, int* __restrict__ p2c, int* __restrict__ keys, int* __restrict__ idx,
+                float4* __restrict__ snapPos, float4* __restrict__ snapVel) {
+    const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const float3 p = load3(pos, i);
+    const int key = cell_index(cell_coord(p.x, cellLength), cell_coord(p.y, cellLength),
+                               cell_coord(p.z, cellLength), cs);
+    p2c[i] = key;
+    keys[i] = key;
+    idx[i] = i;
+    snapPos[i] = make_float4(p.x, p.y, p.z, 0.f);
+    if (vel) { const float3 v = load3(vel, i); snapVel[i] = make_float4(v.x, v.y, v.z, 0.f); }
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_gather(const int* __restrict__ idxSorted, const float4* __restrict__ snapPos,
+         const float4* __restrict__ snapVel, const float* __restrict__ mass, int n,
+         float* __restrict__ pos, float* __restrict__ vel, float4* __restrict__ posm,
+         float4* __restrict__ vel4) {
+    const int s = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (s >= n) return;
+    const int src = idxSorted[s];
+    float4 p = snapPos[src];
+    store3(pos, s, xyz(p));
+    p.w = mass[s];                      // mass is NOT permuted by the reference (Q2): slot s keeps mass[s]
+    posm[s] = p;
+    if (vel) {
+        const float4 v = snapVel[src];
+        store3(vel, s, xyz(v));
+        vel4[s] = v;
+    }
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_cell_start(const int* __restrict__ keysSorted, int n, int ncells, int* __restrict__ cellStart) {
+    const int c = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (c > ncells) return;
+    int lo = 0, hi = n;                 // first s with keysSorted[s] >= c
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keysSorted[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    cellStart[c] = lo;
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_permute(const int* __restrict__ idxSorted, const float* __restrict__ src, float* __restrict__ dst,
+          int width, int n) {
+    const int s = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (s >= n) return;
+    const int from = idxSorted[s];
+    for (int k = 0; k < width; ++k) dst[s * width + k] = src[from * width + k];
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_repack(const float* __restrict__ pos, const float* __restrict__ vel, const float* __restrict__ mass,
+         int n, float4* __restrict__ posm, float4* __restrict__ vel4) {
+    const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const float3 p = load3(pos, i);
+    posm[i] = make_float4(p.x, p.y, p.z, mass[i]);
+    if (vel) { const float3 v = load3(vel, i); vel4[i] = make_float4(v.x, v.y, v.z, 0.f); }
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK) k_fill(float* __restrict__ a, int n, float v) {
+    const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+__global__ void k_rcp(float x, float* out) {
+    float one = 1.0f, r;
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(one), "f"(x));
+    // the hash multiplies by MUFU.RCP(x); div.approx(1,x) = 1 * rcp(x) is that value
+    *out = r;
+}
+
+// abs-sum reduction: fixed-shape two-stage tree (deterministic run to run)
+__global__ void __launch_bounds__(256) k_abs_sum_partial(const float* __restrict__ x, int n, float* __restrict__ partial) {
+    __shared__ float sm[8];
+    float s = 0.f;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) s += fabsf(x[i]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        s = sm[threadIdx.x];
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(256) k_abs_sum_final(const float* __restrict__ partial, int m, float* __restrict__ out) {
+    __shared__ float sm[8];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < m; i += 256) s += partial[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        s = sm[threadIdx.x];
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+        if (threadIdx.x == 0) *out = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T> static cudaError_t dalloc(T** p, size_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, sizeof(T) * (count ? count : 1));
+    return e;
+}
+
+extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, const sphk_grid* grid, void* stream) {
+    if (!out || !grid || max_fluid <= 0 || max_boundary < 0) return SPHK_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return SPHK_ERR_NO_DEVICE; }
+    sphk_ctx* c = new (std::nothrow) sphk_ctx;
+    if (!c) return SPHK_ERR_ALLOC;
+    c->stream = static_cast<cudaStream_t>(stream);
+    c->capF = max_fluid; c->capB = max_boundary;
+    c->cs = make_int3(grid->cell_size[0], grid->cell_size[1], grid->cell_size[2]);
+    c->ncells = c->cs.x * c->cs.y * c->cs.z;
+    c->cellLength = grid->cell_length;
+    c->endBit = 1;
+    while (c->endBit < 32 && (1ll << c->endBit) <= static_cast<long long>(c->ncells)) ++c->endBit;
+    const size_t cap = static_cast<size_t>(max_fluid > max_boundary ? max_fluid : max_boundary);
+    const size_t tot = static_cast<size_t>(max_fluid) + static_cast<size_t>(max_boundary);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = dalloc(&c->keys, cap);
+    if (e == cudaSuccess) e = dalloc(&c->keysSorted, cap);
+    if (e == cudaSuccess) e = dalloc(&c->idx, cap);
+    if (e == cudaSuccess) e = dalloc(&c->idxSorted, cap);
+    if (e == cudaSuccess) e = dalloc(&c->snapA, cap);
+    if (e == cudaSuccess) e = dalloc(&c->snapB, cap);
+    if (e == cudaSuccess) e = dalloc(&c->posm, tot);
+    if (e == cudaSuccess) e = dalloc(&c->vel4, static_cast<size_t>(max_fluid));
+    if (e == cudaSuccess) e = dalloc(&c->aux, tot);
+    if (e == cudaSuccess) e = dalloc(&c->tmpF, 3 * static_cast<size_t>(max_fluid));
+    if (e == cudaSuccess) e = dalloc(&c->partial, 1024);
+    if (e == cudaSuccess) e = dalloc(&c->cnt, static_cast<size_t>(max_fluid));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&c->pinned), 64);
+    if (e == cudaSuccess) {
+        c->cubTempBytes = 0;
+        e = cub::DeviceRadixSort::SortPairs(nullptr, c->cubTempBytes, c->keys, c->keysSorted, c->idx, c->idxSorted,
+                                            static_cast<int>(cap), 0, c->endBit, c->stream);
+        if (e == cudaSuccess) e = cudaMalloc(&c->cubTemp, c->cubTempBytes ? c->cubTempBytes : 1);
+    }
+    if (e != cudaSuccess) { sphk_destroy(c); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? SPHK_ERR_ALLOC : static_cast<int>(e); }
+    *out = c;
+    return SPHK_OK;
+}
+
+extern "C" void sphk_destroy(sphk_ctx* c) {
+    if (!c) return;
+    cudaFree(c->keys); cudaFree(c->keysSorted); cudaFree(c->idx); cudaFree(c->idxSorted);
+    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->posm); cudaFree(c->vel4); cudaFree(c->aux);
+    cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    delete c;
+}
+
+extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
+    if (!c) return SPHK_ERR_INVALID;
+    switch (option) {
+    case SPHK_OPT_NEIGHBOR_LIST: c->useList = value != 0; return SPHK_OK;
+    case SPHK_OPT_LIST_CAPACITY:
+        if (value < 8 || value > 1024) return SPHK_ERR_INVALID;
+        if (value != c->kmax) {
+            if (c->nbr) { cudaStreamSynchronize(c->stream); cudaFree(c->nbr); c->nbr = nullptr; }
+            c->kmax = value; c->listEpoch = ~0ull;
+        }
+        return SPHK_OK;
+    case SPHK_OPT_TILE_SWEEP: c->useTile = value != 0; return SPHK_OK;
+    default: return SPHK_ERR_INVALID;
+    }
+}
+
+extern "C" int sphk_synchronize(sphk_ctx* c) {
+    if (!c) return SPHK_ERR_INVALID;
+    SPHK_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+extern "C" const char* sphk_error_string(int code) {
+    switch (code) {
+    case SPHK_OK: return "ok";
+    case SPHK_ERR_INVALID: return "sphk: invalid argument";
+    case SPHK_ERR_NO_DEVICE: return "sphk: no CUDA device (libsphk has no CPU path)";
+    case SPHK_ERR_CAPACITY: return "sphk: particle count exceeds context capacity";
+    case SPHK_ERR_STATE: return "sphk: call order violated (neighbour search missing or stale scene)";
+    case SPHK_ERR_ALLOC: return "sphk: device allocation failed";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "sphk: unknown error";
+    }
+}
+
+extern "C" long long sphk_launch_count(const sphk_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int sphk_device_rcp(sphk_ctx* c, float x, float* out_host) {
+    if (!c || !out_host) return SPHK_ERR_INVALID;
+    k_rcp<<<1, 1, 0, c->stream>>>(x, c->partial);
+    c->launches++;
+    SPHK_CUDA_TRY(cudaMemcpyAsync(c->pinned, c->partial, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SPHK_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out_host = *c->pinned;
+    return SPHK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int sphk_neighbor_search(sphk_ctx* c, int which, const sphk_particles* p, int* cell_start) {
+    if (!c || !p || !cell_start || !p->pos || !p->mass || !p->particle2cell || p->n <= 0) return SPHK_ERR_INVALID;
+    const bool fluid = which == 0;
+    if (fluid && !p->vel) return SPHK_ERR_INVALID;
+    const int n = p->n;
+    if (n > (fluid ? c->capF : c->capB)) return SPHK_ERR_CAPACITY;
+    const int off = fluid ? 0 : c->capF;
+    cudaStream_t st = c->stream;
+    k_hash_snapshot<<<sphk_blocks(n), SPHK_BLOCK, 0, st>>>(p->pos, p->vel, n, c->cellLength, c->cs, p->particle2cell,
+                                                          c->keys, c->idx, c->snapA, c->snapB);
+    size_t tb = c->cubTempBytes;
+    SPHK_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cubTemp, tb, c->keys, c->keysSorted, c->idx, c->idxSorted, n, 0,
+                                                  c->endBit, st));
+    k_gather<<<sphk_blocks(n), SPHK_BLOCK, 0, st>>>(c->idxSorted, c->snapA, c->snapB, p->mass, n, p->pos, p->vel,
+                                                   c->posm + off, fluid ? c->vel4 : nullptr);
+    k_cell_start<<<sphk_blocks(c->ncells + 1), SPHK_BLOCK, 0, st>>>(c->keysSorted, n, c->ncells, cell_start);
+    c->launches += 3 + 4;   // 3 own kernels + CUB onesweep (histogram, scan, <=3 passes): counted as 4
+    if (fluid) { c->nF = n; c->fluidSearched = true; c->permValid = true; c->searchEpoch++; c->posDirty = false; }
+    else { c->nB = n; c->boundarySearched = true; c->listEpoch = ~0ull; c->permValid = false; }
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+extern "C" int sphk_permute(sphk_ctx* c, float* array, int width, int n) {
+    if (!c || !array || (width != 1 && width != 3)) return SPHK_ERR_INVALID;
+    if (!c->permValid || n != c->nF) return SPHK_ERR_STATE;
+    k_permute<<<sphk_blocks(n), SPHK_BLOCK, 0, c->stream>>>(c->idxSorted, array, c->tmpF, width, n);
+    c->launches++;
+    SPHK_CUDA_TRY(cudaMemcpyAsync(array, c->tmpF, sizeof(float) * static_cast<size_t>(n) * width,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+    return SPHK_OK;
+}
+
+extern "C" int sphk_refresh(sphk_ctx* c, const sphk_scene* s) {
+    if (!c || !s) return SPHK_ERR_INVALID;
+    if (!c->fluidSearched || s->fluid.n != c->nF) return SPHK_ERR_STATE;
+    k_repack<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(s->fluid.pos, s->fluid.vel, s->fluid.mass, c->nF,
+                                                              c->posm, c->vel4);
+    c->launches++;
+    c->posDirty = true;
+    if (c->boundarySearched && s->boundary.pos && s->boundary.n == c->nB) {
+        k_repack<<<sphk_blocks(c->nB), SPHK_BLOCK, 0, c->stream>>>(s->boundary.pos, nullptr, s->boundary.mass, c->nB,
+                                                                  c->posm + c->capF, nullptr);
+        c->launches++;
+    }
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+extern "C" int sphk_fill(sphk_ctx* c, float* array, int n, float value) {
+    if (!c || !array || n < 0) return SPHK_ERR_INVALID;
+    if (n == 0) return SPHK_OK;
+    k_fill<<<sphk_blocks(n), SPHK_BLOCK, 0, c->stream>>>(array, n, value);
+    c->launches++;
+    // the fluid mass fill of SPHSystem.cu:73 happens after the first fluid search packed mass into the
+    // shadow: keep the shadow coherent when the filled array is a bound mass array
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+extern "C" int sphk_copy(sphk_ctx* c, float* dst, const float* src, int n_floats) {
+    if (!c || !dst || !src || n_floats < 0) return SPHK_ERR_INVALID;
+    SPHK_CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(float) * static_cast<size_t>(n_floats), cudaMemcpyDeviceToDevice, c->stream));
+    return SPHK_OK;
+}
+
+extern "C" int sphk_reduce_abs_sum(sphk_ctx* c, const float* x, int n, float* host_out) {
+    if (!c || !x || !host_out || n < 0) return SPHK_ERR_INVALID;
+    int blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1024) blocks = 1024;
+    k_abs_sum_partial<<<blocks, 256, 0, c->stream>>>(x, n, c->partial);
+    k_abs_sum_final<<<1, 256, 0, c->stream>>>(c->partial, blocks, c->partial);
+    c->launches += 2;
+    SPHK_CUDA_TRY(cudaMemcpyAsync(c->pinned, c->partial, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SPHK_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *host_out = *c->pinned;
+    return SPHK_OK;
+}
+
+extern "C" int sphk_get_permutation(sphk_ctx* c, int* perm_out, int n) {
+    if (!c || !perm_out) return SPHK_ERR_INVALID;
+    if (!c->permValid || n != c->nF) return SPHK_ERR_STATE;
+    SPHK_CUDA_TRY(cudaMemcpyAsync(perm_out, c->idxSorted, sizeof(int) * static_cast<size_t>(n), cudaMemcpyDeviceToDevice, c->stream));
+    return SPHK_OK;
+}

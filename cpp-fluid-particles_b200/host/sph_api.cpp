@@ -1,0 +1,338 @@
+// sph_api.cpp -- host-side orchestration of one simulation step over the libsphk C-ABI.
+// Each method states the reference code whose behaviour it reproduces (/root/reference/src/...).
+// No device code here: this file is compiled by g++.
+#include "sph_api.hpp"
+
+#include <algorithm>
+#include <limits>
+
+using sphb200::check;
+
+// ================================================================================================
+// Engine
+// ================================================================================================
+namespace sphb200 {
+Engine::Engine(int maxFluid, int maxBoundary, int3 cellSize, float cellLength) {
+    // blocking stream: legacy-default-stream work of the caller (DArray memset, cudaMemcpy through the
+    // raw accessors) orders with the engine's work exactly as it does in the single-stream reference
+    CUDA_CALL(cudaStreamCreate(&stream_));
+    sphk_grid g;
+    g.cell_size[0] = cellSize.x; g.cell_size[1] = cellSize.y; g.cell_size[2] = cellSize.z;
+    g.cell_length = cellLength;
+    const int rc = sphk_create(&ctx_, maxFluid, maxBoundary, &g, stream_);
+    if (rc != 0) {
+        // no CPU fallback: a missing device / failed allocation is reported and leaves the system inert
+        printf("sphk_create failed: %s (%d)\n", sphk_error_string(rc), rc);
+        ctx_ = nullptr;
+    }
+}
+Engine::~Engine() {
+    if (ctx_) { sphk_synchronize(ctx_); sphk_destroy(ctx_); }
+    if (stream_) cudaStreamDestroy(stream_);
+}
+}  // namespace sphb200
+
+// ================================================================================================
+// Particles (Particles.h:22-25, Particles.cu:28-36)
+// ================================================================================================
+Particles::Particles(const std::vector<float3>& p) : pos(p.size()), vel(p.size()) {
+    CUDA_CALL(cudaMemcpy(pos.addr(), p.data(), sizeof(float3) * p.size(), cudaMemcpyHostToDevice));
+}
+
+void Particles::advect(float dt) {
+    // pos += dt * vel.  Not on the engine's hot path (BasicSPHSolver::advect uses the fused
+    // sphk_advect); kept for API parity.  Moves particles behind the engine's back -> shadows stale.
+    if (engine_ && engine_->ok()) {
+        sphk_synchronize(engine_->ctx());
+        engine_->shadowsStale = true;
+    }
+    const size_t n = size();
+    std::vector<float3> hp(n), hv(n);
+    CUDA_CALL(cudaMemcpy(hp.data(), pos.addr(), sizeof(float3) * n, cudaMemcpyDeviceToHost));
+    CUDA_CALL(cudaMemcpy(hv.data(), vel.addr(), sizeof(float3) * n, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) {
+        hp[i].x = hp[i].x + dt * hv[i].x; hp[i].y = hp[i].y + dt * hv[i].y; hp[i].z = hp[i].z + dt * hv[i].z;
+    }
+    CUDA_CALL(cudaMemcpy(pos.addr(), hp.data(), sizeof(float3) * n, cudaMemcpyHostToDevice));
+}
+
+// ================================================================================================
+// BasicSPHSolver (BasicSPHSolver.cu)
+// ================================================================================================
+bool BasicSPHSolver::beginStep(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
+                               const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float radius,
+                               bool neighborList) {
+    const auto& eng = fluids->engine();
+    if (!eng || !eng->ok()) {
+        printf("SPH solver: particles are not bound to a B200 engine (construct them through SPHSystem)\n");
+        current_.ctx = nullptr;
+        return false;
+    }
+    current_.ctx = eng->ctx();
+    current_.abi.fluid = fluids->abi();
+    current_.abi.boundary = boundaries->abi();
+    current_.abi.cell_start_fluid = cellStartFluid.addr();
+    current_.abi.cell_start_boundary = cellStartBoundary.addr();
+    current_.abi.radius = radius;
+    check(sphk_set_option(current_.ctx, SPHK_OPT_NEIGHBOR_LIST, neighborList ? 1 : 0), "sphk_set_option");
+    if (eng->shadowsStale) { check(sphk_refresh(current_.ctx, &current_.abi), "sphk_refresh"); eng->shadowsStale = false; }
+    return true;
+}
+
+// BasicSPHSolver::step, BasicSPHSolver.cu:237-260
+void BasicSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
+                          const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
+                          int3 cellSize, float cellLength, float radius, float dt, float rho0, float rhoB, float stiff,
+                          float visc, float3 G, float surfaceTensionIntensity, float airPressure) {
+    if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, true)) return;
+    force(fluids, dt, G);
+    diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, visc, dt);
+    if (surfaceTensionIntensity > EPSILON || airPressure > EPSILON)
+        handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
+                      dt, surfaceTensionIntensity, airPressure);
+    project(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, stiff, cellSize, cellLength, radius, dt);
+    advect(fluids, dt, spaceSize);
+}
+
+// :227-235
+void BasicSPHSolver::force(std::shared_ptr<SPHParticles>&, float dt, float3 G) {
+    if (!current_.ctx) return;
+    const float g[3] = {G.x, G.y, G.z};
+    check(sphk_gravity(current_.ctx, &current_.abi, dt, g), "sphk_gravity");
+}
+
+// :98-101
+void BasicSPHSolver::advect(std::shared_ptr<SPHParticles>&, float dt, float3 spaceSize) {
+    if (!current_.ctx) return;
+    const float sp[3] = {spaceSize.x, spaceSize.y, spaceSize.z};
+    check(sphk_advect(current_.ctx, &current_.abi, dt, sp), "sphk_advect");
+}
+
+// :167-181
+void BasicSPHSolver::project(std::shared_ptr<SPHParticles>&, const std::shared_ptr<SPHParticles>&, const DArray<int>&,
+                             const DArray<int>&, float rho0, float stiff, int3, float, float, float dt) {
+    if (!current_.ctx) return;
+    check(sphk_density(current_.ctx, &current_.abi), "sphk_density");
+    check(sphk_pressure(current_.ctx, &current_.abi, rho0, stiff), "sphk_pressure");
+    check(sphk_pressure_force(current_.ctx, &current_.abi, dt), "sphk_pressure_force");
+}
+
+// :211-225
+void BasicSPHSolver::diffuse(std::shared_ptr<SPHParticles>&, const DArray<int>&, int3, float, float rho0, float,
+                             float visc, float dt) {
+    if (!current_.ctx) return;
+    check(sphk_viscosity(current_.ctx, &current_.abi, reinterpret_cast<float*>(bufferFloat3.addr()), rho0, visc, dt),
+          "sphk_viscosity");
+}
+
+// :262-275
+void BasicSPHSolver::handleSurface(std::shared_ptr<SPHParticles>&, const std::shared_ptr<SPHParticles>&,
+                                   const DArray<int>&, const DArray<int>&, float rho0, float rhoB, int3, float, float,
+                                   float dt, float surfaceTensionIntensity, float airPressure) {
+    if (!current_.ctx) return;
+    float* cg = reinterpret_cast<float*>(bufferFloat3.addr());
+    check(sphk_color_grad(current_.ctx, &current_.abi, cg, rho0, rhoB), "sphk_color_grad");
+    check(sphk_surface(current_.ctx, &current_.abi, cg, dt, rho0, surfaceTensionIntensity, airPressure), "sphk_surface");
+}
+
+// ================================================================================================
+// DFSPHSolver (DFSPHSolver.cu)
+// ================================================================================================
+// DFSPHSolver::step, DFSPHSolver.cu:33-72
+void DFSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
+                       const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
+                       int3 cellSize, float cellLength, float radius, float dt, float rho0, float rhoB, float,
+                       float visc, float3 G, float surfaceTensionIntensity, float airPressure) {
+    if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, true)) return;
+    const int num = static_cast<int>(fluids->size());
+    check(sphk_dfsph_density_alpha(current_.ctx, &current_.abi, alpha.addr()), "sphk_dfsph_density_alpha");
+    itDiv_ = correctDivergenceError(rho0, dt, divergenceErrorThreshold, maxIter, num);
+    force(fluids, dt, G);
+    BasicSPHSolver::diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, visc, dt);
+    if (surfaceTensionIntensity > EPSILON || airPressure > EPSILON)
+        handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
+                      dt, surfaceTensionIntensity, airPressure);
+    itDen_ = project(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, cellSize, cellLength, radius, dt,
+                     densityErrorThreshold, maxIter);
+    advect(fluids, dt, spaceSize);
+}
+
+// DFSPHSolver::correctDivergenceError, DFSPHSolver.cu:331-363.  With a negative threshold the loop test
+// `totalError > thr*num*rho0` is true for every possible error sum, so the (host-synchronising)
+// reduction is skipped: same iteration count as the reference, no pipeline bubble (Q11).
+int DFSPHSolver::correctDivergenceError(float rho0, float dt, float errorThreshold, int maxIter_, int num) {
+    auto totalError = std::numeric_limits<float>::max();
+    auto iter = 0;
+    sphk_ctx* ctx = current_.ctx;
+    check(sphk_dfsph_div_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0),
+          "sphk_dfsph_div_error");
+    while ((iter < 1 || totalError > errorThreshold * num * rho0) && iter < maxIter_) {
+        check(sphk_dfsph_div_correct(ctx, &current_.abi, bufferFloat.addr()), "sphk_dfsph_div_correct");
+        check(sphk_dfsph_div_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0),
+              "sphk_dfsph_div_error");
+        ++iter;
+        if (errorThreshold >= 0.0f) check(sphk_reduce_abs_sum(ctx, error.addr(), num, &totalError), "sphk_reduce_abs_sum");
+    }
+    return iter;
+}
+
+// DFSPHSolver::project, DFSPHSolver.cu:160-210
+int DFSPHSolver::project(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>&, const DArray<int>&,
+                         const DArray<int>&, float rho0, int3, float, float, float dt, float errorThreshold,
+                         int maxIter_) {
+    if (!current_.ctx) return 0;
+    sphk_ctx* ctx = current_.ctx;
+    const int num = static_cast<int>(fluids->size());
+    auto totalError = std::numeric_limits<float>::max();
+    auto iter = 0;
+    // warm stiffness of the previous step follows its particle (:170-171)
+    check(sphk_permute(ctx, denWarmStiff.addr(), 1, num), "sphk_permute");
+    check(sphk_dfsph_den_correct(ctx, &current_.abi, denWarmStiff.addr(), dt), "sphk_dfsph_den_correct");
+    check(sphk_dfsph_den_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0, nullptr),
+          "sphk_dfsph_den_error");
+    check(sphk_copy(ctx, denWarmStiff.addr(), bufferFloat.addr(), num), "sphk_copy");     // :185
+    while ((iter < 2 || totalError > errorThreshold * num * rho0) && iter < maxIter_) {
+        check(sphk_dfsph_den_correct(ctx, &current_.abi, bufferFloat.addr(), dt), "sphk_dfsph_den_correct");
+        check(sphk_dfsph_den_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0,
+                                   denWarmStiff.addr()),
+              "sphk_dfsph_den_error");                                                    // + :199-203 fused
+        ++iter;
+        if (iter >= 2 && errorThreshold >= 0.0f)
+            check(sphk_reduce_abs_sum(ctx, error.addr(), num, &totalError), "sphk_reduce_abs_sum");
+    }
+    return iter;
+}
+
+// ================================================================================================
+// PBDSolver (PBDSolver.cu)
+// ================================================================================================
+// PBDSolver::step, PBDSolver.cu:34-73
+void PBDSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
+                     const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
+                     int3 cellSize, float cellLength, float radius, float dt, float rho0, float rhoB, float, float,
+                     float3 G, float surfaceTensionIntensity, float airPressure) {
+    if (!posLastInitialized) {
+        if (fluids->engine() && fluids->engine()->ok()) sphk_synchronize(fluids->engine()->ctx());
+        initializePosLast(fluids->getPos());
+        throw "PBD: The last position of fluids is initialized.";     // Q6, PBDSolver.cu:44-47
+    }
+    // positions move inside the step (Q7): the per-step neighbour list does not apply
+    if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, false)) return;
+    updateNeighborhood(fluids);
+    project(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, cellSize, spaceSize, cellLength, radius, maxIter);
+    check(sphk_pbd_velocity_from_positions(current_.ctx, &current_.abi, reinterpret_cast<float*>(fluidPosLast.addr()), dt),
+          "sphk_pbd_velocity_from_positions");
+    diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, xSPH_c);
+    if (surfaceTensionIntensity > EPSILON || airPressure > EPSILON)
+        handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
+                      dt, surfaceTensionIntensity, airPressure);
+    force(fluids, dt, G);
+    predict(fluids, dt, spaceSize);
+}
+
+// :75-79
+void PBDSolver::predict(std::shared_ptr<SPHParticles>& fluids, float dt, float3 spaceSize) {
+    check(sphk_copy(current_.ctx, reinterpret_cast<float*>(fluidPosLast.addr()),
+                    reinterpret_cast<const float*>(fluids->getPosPtr()), 3 * static_cast<int>(fluids->size())),
+          "sphk_copy");
+    advect(fluids, dt, spaceSize);
+}
+
+// :81-87
+void PBDSolver::updateNeighborhood(const std::shared_ptr<SPHParticles>& particles) {
+    check(sphk_permute(current_.ctx, reinterpret_cast<float*>(fluidPosLast.addr()), 3, static_cast<int>(particles->size())),
+          "sphk_permute");
+}
+
+// :117-125
+void PBDSolver::diffuse(std::shared_ptr<SPHParticles>&, const DArray<int>&, int3, float, float rho0, float, float visc) {
+    check(sphk_pbd_xsph(current_.ctx, &current_.abi, visc, rho0), "sphk_pbd_xsph");
+}
+
+// :225-258
+int PBDSolver::project(std::shared_ptr<SPHParticles>&, const std::shared_ptr<SPHParticles>&, const DArray<int>&,
+                       const DArray<int>&, float rho0, int3, float3 spaceSize, float, float, int maxIter_) {
+    const float sp[3] = {spaceSize.x, spaceSize.y, spaceSize.z};
+    auto iter = 0;
+    while (iter < maxIter_) {
+        check(sphk_pbd_density_lambda(current_.ctx, &current_.abi, bufferFloat.addr(), rho0, relaxation),
+              "sphk_pbd_density_lambda");
+        check(sphk_pbd_delta_pos_apply(current_.ctx, &current_.abi, bufferFloat.addr(),
+                                       reinterpret_cast<float*>(bufferFloat3.addr()), rho0, sp),
+              "sphk_pbd_delta_pos_apply");
+        ++iter;
+    }
+    return iter;
+}
+
+// ================================================================================================
+// SPHSystem (SPHSystem.cu)
+// ================================================================================================
+SPHSystem::SPHSystem(std::shared_ptr<SPHParticles>& fluidParticles, std::shared_ptr<SPHParticles>& boundaryParticles,
+                     std::shared_ptr<BaseSolver>& solver, const float3 spaceSize, const float sphCellLength,
+                     const float sphSmoothingRadius, const float dt, const float sphM0, const float sphRho0,
+                     const float sphRhoBoundary, const float sphStiff, const float sphVisc,
+                     const float sphSurfaceTensionIntensity, const float sphAirPressure, const float3 sphG,
+                     const int3 cellSize)
+    // the caller's three shared_ptrs are moved from, as in the reference (SPHSystem.cu:50-51)
+    : _fluids(std::move(fluidParticles)), _boundaries(std::move(boundaryParticles)), _solver(std::move(solver)),
+      cellStartFluid(cellSize.x * cellSize.y * cellSize.z + 1), cellStartBoundary(cellSize.x * cellSize.y * cellSize.z + 1),
+      _spaceSize(spaceSize), _sphSmoothingRadius(sphSmoothingRadius), _sphCellLength(sphCellLength), _dt(dt),
+      _sphRho0(sphRho0), _sphRhoBoundary(sphRhoBoundary), _sphStiff(sphStiff), _sphG(sphG), _sphVisc(sphVisc),
+      _sphSurfaceTensionIntensity(sphSurfaceTensionIntensity), _sphAirPressure(sphAirPressure), _cellSize(cellSize) {
+    _engine = std::make_shared<sphb200::Engine>(fluidSize(), boundarySize(), cellSize, sphCellLength);
+    _fluids->bindEngine(_engine);
+    _boundaries->bindEngine(_engine);
+    CUDA_CALL(cudaEventCreate(&_evStart));
+    CUDA_CALL(cudaEventCreate(&_evStop));
+    if (!_engine->ok()) return;
+    // SPHSystem.cu:68-76
+    neighborSearch(_boundaries, cellStartBoundary);
+    computeBoundaryMass();
+    check(sphk_fill(_engine->ctx(), _fluids->getMassPtr(), fluidSize(), sphM0), "sphk_fill");
+    neighborSearch(_fluids, cellStartFluid);
+    step();
+}
+
+SPHSystem::~SPHSystem() noexcept {
+    if (_engine && _engine->ok()) sphk_synchronize(_engine->ctx());
+    if (_evStart) cudaEventDestroy(_evStart);
+    if (_evStop) cudaEventDestroy(_evStop);
+}
+
+// SPHSystem.cu:107-112
+void SPHSystem::computeBoundaryMass() {
+    const sphk_particles b = _boundaries->abi();
+    check(sphk_boundary_mass(_engine->ctx(), &b, cellStartBoundary.addr(), _sphRhoBoundary, _sphSmoothingRadius),
+          "sphk_boundary_mass");
+}
+
+// SPHSystem.cu:114-127
+void SPHSystem::neighborSearch(const std::shared_ptr<SPHParticles>& particles, DArray<int>& cellStart) {
+    const sphk_particles p = particles->abi();
+    const int which = (particles.get() == _boundaries.get()) ? 1 : 0;
+    check(sphk_neighbor_search(_engine->ctx(), which, &p, cellStart.addr()), "sphk_neighbor_search");
+}
+
+// SPHSystem.cu:129-158
+float SPHSystem::step() {
+    if (!_engine->ok()) return 0.0f;
+    cudaStream_t st = _engine->stream();
+    CUDA_CALL(cudaEventRecord(_evStart, st));
+    neighborSearch(_fluids, cellStartFluid);
+    try {
+        _solver->step(_fluids, _boundaries, cellStartFluid, cellStartBoundary, _spaceSize, _cellSize, _sphCellLength,
+                      _sphSmoothingRadius, _dt, _sphRho0, _sphRhoBoundary, _sphStiff, _sphVisc, _sphG,
+                      _sphSurfaceTensionIntensity, _sphAirPressure);
+        check(sphk_synchronize(_engine->ctx()), "step");
+    } catch (const char* s) {
+        std::cout << s << "\n";
+    } catch (...) {
+        std::cout << "Unknown Exception at " << __FILE__ << ": line " << __LINE__ << "\n";
+    }
+    float milliseconds = 0.0f;
+    CUDA_CALL(cudaEventRecord(_evStop, st));
+    CUDA_CALL(cudaEventSynchronize(_evStop));
+    CUDA_CALL(cudaEventElapsedTime(&milliseconds, _evStart, _evStop));
+    return milliseconds;
+}

@@ -1,0 +1,178 @@
+/* sphk.h -- C-ABI of the B200-native SPH kernel library (libsphk.so, sm_100a).
+ *
+ * The reference (zhai-xiao/CPP-Fluid-Particles) has no FFI/plugin boundary: its boundary is the C++
+ * class API SPHSystem / BaseSolver / SPHParticles / DArray compiled into one executable.  This
+ * header is the boundary a maintainer binds to: ONE entry point per reference launch site on the
+ * hot path SPHSystem::step() (each declaration cites the reference code it replaces, paths relative
+ * to /root/reference/src).  The reference-shaped C++ classes in cpp-fluid-particles_b200/host/ are
+ * written purely on top of these calls.
+ *
+ * Conventions
+ *  - Plain C: raw DEVICE pointers, ints, floats, PODs.  No torch / thrust / C++ types.
+ *  - "float3 arrays" are packed xyz triplets, 12-byte stride, exactly the reference's float3 DArrays.
+ *  - Every function returns 0 on success or a negative SPHK_ERR_* / positive cudaError_t value, and
+ *    never throws.  Nothing synchronises the host unless stated (the reference syncs on every Thrust
+ *    call; here only sphk_reduce_abs_sum and sphk_synchronize do).
+ *  - All work is enqueued on the stream given to sphk_create (a cudaStream_t passed as void*).
+ *  - There is NO CPU fallback: without a CUDA device sphk_create fails with SPHK_ERR_NO_DEVICE.
+ *  - The library never allocates or frees API-visible arrays; sphk_ctx owns only scratch (sort
+ *    buffers, packed float4 shadows of the particle attributes, neighbour lists).
+ *
+ * Shadow coherence rule: sphk_neighbor_search() packs the particle set into float4 shadows that the
+ * sweep kernels read; every sphk_* call that changes pos / vel writes both the API array and the
+ * shadow.  If the caller edits pos / vel itself between calls it must call sphk_neighbor_search (or
+ * sphk_refresh) before the next sweep.
+ */
+#ifndef SPHK_H_
+#define SPHK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHK_VERSION 1
+
+enum {
+    SPHK_OK = 0,
+    SPHK_ERR_INVALID = -1,    /* bad argument */
+    SPHK_ERR_NO_DEVICE = -2,  /* no CUDA device / driver: there is no CPU path */
+    SPHK_ERR_CAPACITY = -3,   /* n exceeds the capacity given to sphk_create */
+    SPHK_ERR_STATE = -4,      /* call order violated (e.g. sweep before neighbour search) */
+    SPHK_ERR_ALLOC = -5
+};
+
+typedef struct sphk_ctx sphk_ctx;
+
+/* Uniform grid, CUDAFunctions.cuh:64-78: cell (x,y,z) -> (x*cs.y + y)*cs.z + z, z fastest. */
+typedef struct sphk_grid {
+    int   cell_size[3];
+    float cell_length;
+} sphk_grid;
+
+/* One SPHParticles object (SPHParticles.h:56-59 + Particles.h:47-48): device pointers. */
+typedef struct sphk_particles {
+    float* pos;            /* float3[n]   getPosPtr()          */
+    float* vel;            /* float3[n]   getVelPtr()  (NULL allowed for boundaries) */
+    float* mass;           /* float[n]    getMassPtr()         */
+    float* density;        /* float[n]    getDensityPtr()      */
+    float* pressure;       /* float[n]    getPressurePtr()     */
+    int*   particle2cell;  /* int[n]      getParticle2Cell()   */
+    int    n;
+} sphk_particles;
+
+/* What every solver step receives (BaseSolver.h:22-26): both particle sets + their cell ranges. */
+typedef struct sphk_scene {
+    sphk_particles fluid;
+    sphk_particles boundary;
+    const int* cell_start_fluid;     /* int[ncells+1] */
+    const int* cell_start_boundary;  /* int[ncells+1] */
+    float radius;                    /* sphSmoothingRadius */
+} sphk_scene;
+
+enum {
+    SPHK_OPT_NEIGHBOR_LIST = 1,  /* 1: sweeps walk a per-step neighbour list while positions are
+                                    unchanged since the search (WCSPH, DFSPH); 0: always walk the
+                                    27 cells (PBD moves positions inside a step, Q7).  default 1 */
+    SPHK_OPT_LIST_CAPACITY = 2,  /* max neighbours kept per particle; particles with more fall back
+                                    to the cell walk individually.  default 96 */
+    SPHK_OPT_TILE_SWEEP = 3      /* 1: cell-walk sweeps use the TMA-staged shared-memory tile kernel */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int  sphk_create(sphk_ctx** ctx, int max_fluid, int max_boundary, const sphk_grid* grid, void* stream);
+void sphk_destroy(sphk_ctx* ctx);
+int  sphk_set_option(sphk_ctx* ctx, int option, int value);
+int  sphk_synchronize(sphk_ctx* ctx);
+const char* sphk_error_string(int code);
+/* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
+long long sphk_launch_count(const sphk_ctx* ctx);
+/* rcp.approx(cell_length) as the device computes it (bit pattern as float): lets a CPU checker
+ * reproduce the GPU cell hash bit-for-bit */
+int  sphk_device_rcp(sphk_ctx* ctx, float x, float* out_host);
+
+/* ---- neighbour search: SPHSystem::neighborSearch, SPHSystem.cu:114-127 ------------------------
+ * Replaces mapParticles2Cells_CUDA (CUDAFunctions.cuh:72-78), two thrust::sort_by_key with float3
+ * payloads (SPHSystem.cu:119,121), thrust::fill + countingInCell_CUDA + thrust::exclusive_scan
+ * (SPHSystem.cu:123-125).  Bit-exact contract: particle2cell (left in PRE-sort order, quirk Q2), the
+ * stable-sort permutation applied to pos and vel, and cell_start[ncells+1].
+ * which = 0: the fluid set (p = &scene->fluid, cell_start = cell_start_fluid);
+ * which = 1: the boundary set (searched once at construction, SPHSystem.cu:69). */
+int sphk_neighbor_search(sphk_ctx* ctx, int which, const sphk_particles* p, int* cell_start);
+
+/* Applies the permutation of the last fluid neighbour search to a solver-private history array, in
+ * place: replaces DFSPHSolver.cu:170-171 (denWarmStiff, width 1) and PBDSolver.cu:84-85
+ * (fluidPosLast, width 3), which re-sort with particle2cell as keys and rely on sort stability. */
+int sphk_permute(sphk_ctx* ctx, float* array, int width, int n);
+
+/* Re-packs the shadows from the API arrays without re-sorting (after caller-side edits). */
+int sphk_refresh(sphk_ctx* ctx, const sphk_scene* scene);
+
+/* computeBoundaryMass_CUDA, SPHSystem.cu:79-112: mass_b = rhoB / max(eps, sum_k W(|x_b - x_k|)). */
+int sphk_boundary_mass(sphk_ctx* ctx, const sphk_particles* boundary, const int* cell_start_boundary,
+                       float rho_boundary, float radius);
+
+/* thrust::fill, SPHSystem.cu:73 / BasicSPHSolver.cu:78 */
+int sphk_fill(sphk_ctx* ctx, float* array, int n, float value);
+
+/* ---- WCSPH: BasicSPHSolver.cu -------------------------------------------------------------- */
+/* force(): vel += dt*G, BasicSPHSolver.cu:227-235 */
+int sphk_gravity(sphk_ctx* ctx, const sphk_scene* s, float dt, const float G[3]);
+/* viscosity_CUDA + thrust::transform(vel += deltaV), BasicSPHSolver.cu:183-225.  delta_v (float3[n])
+ * is the reference's bufferFloat3 and receives visc*a*dt as in the reference. */
+int sphk_viscosity(sphk_ctx* ctx, const sphk_scene* s, float* delta_v, float rho0, float visc, float dt);
+/* computeColorGrad_CUDA, BasicSPHSolver.cu:277-330 */
+int sphk_color_grad(sphk_ctx* ctx, const sphk_scene* s, float* color_grad, float rho0, float rho_boundary);
+/* surfaceTensionAndAirPressure_CUDA, BasicSPHSolver.cu:332-381 */
+int sphk_surface(sphk_ctx* ctx, const sphk_scene* s, const float* color_grad, float dt, float rho0,
+                 float surface_tension, float air_pressure);
+/* thrust::fill(density,0) + computeDensity_CUDA, BasicSPHSolver.cu:32-83 */
+int sphk_density(sphk_ctx* ctx, const sphk_scene* s);
+/* computePressure_CUDA, BasicSPHSolver.cu:103-111 */
+int sphk_pressure(sphk_ctx* ctx, const sphk_scene* s, float rho0, float stiff);
+/* pressureForce_CUDA, BasicSPHSolver.cu:113-165 */
+int sphk_pressure_force(sphk_ctx* ctx, const sphk_scene* s, float dt);
+/* Particles::advect (Particles.cu:28-36) + enforceBoundary_CUDA(pos,vel) (BasicSPHSolver.cu:85-101) */
+int sphk_advect(sphk_ctx* ctx, const sphk_scene* s, float dt, const float space[3]);
+
+/* ---- DFSPH: DFSPHSolver.cu ----------------------------------------------------------------- */
+/* computeDensityAlpha_CUDA, DFSPHSolver.cu:212-259 */
+int sphk_dfsph_density_alpha(sphk_ctx* ctx, const sphk_scene* s, float* alpha);
+/* computeDivergenceError_CUDA, DFSPHSolver.cu:261-306 */
+int sphk_dfsph_div_error(sphk_ctx* ctx, const sphk_scene* s, const float* alpha, float* error,
+                         float* stiff, float dt, float rho0);
+/* correctDivergenceError_CUDA, DFSPHSolver.cu:308-329 */
+int sphk_dfsph_div_correct(sphk_ctx* ctx, const sphk_scene* s, const float* stiff);
+/* computeDensityError_CUDA, DFSPHSolver.cu:74-116.  warm_accumulate (may be NULL) additionally does
+ * warm[i] += stiff[i], i.e. the thrust::transform of DFSPHSolver.cu:199-203 fused in. */
+int sphk_dfsph_den_error(sphk_ctx* ctx, const sphk_scene* s, const float* alpha, float* error,
+                         float* stiff, float dt, float rho0, float* warm_accumulate);
+/* correctDensityError_CUDA, DFSPHSolver.cu:118-158 */
+int sphk_dfsph_den_correct(sphk_ctx* ctx, const sphk_scene* s, const float* stiff, float dt);
+/* thrust::reduce(error, abs_plus), DFSPHSolver.cu:206,360.  Synchronises; result to *host_out. */
+int sphk_reduce_abs_sum(sphk_ctx* ctx, const float* x, int n, float* host_out);
+/* cudaMemcpy D2D of a float array, DFSPHSolver.cu:185 */
+int sphk_copy(sphk_ctx* ctx, float* dst, const float* src, int n_floats);
+
+/* ---- PBD: PBDSolver.cu --------------------------------------------------------------------- */
+/* computeDensityLambda_CUDA, PBDSolver.cu:127-168 (incl. the `bool rho0` quirk Q4) */
+int sphk_pbd_density_lambda(sphk_ctx* ctx, const sphk_scene* s, float* lambda, float rho0, float relaxation);
+/* computeDeltaPos_CUDA + thrust::transform(pos += dpos) + enforceBoundary_CUDA(pos),
+ * PBDSolver.cu:170-256.  delta_pos (float3[n]) receives dp/rho0 as in the reference. */
+int sphk_pbd_delta_pos_apply(sphk_ctx* ctx, const sphk_scene* s, const float* lambda, float* delta_pos,
+                             float rho0, const float space[3]);
+/* thrust::transform(vel = (pos - posLast)/dt), PBDSolver.cu:55-60 */
+int sphk_pbd_velocity_from_positions(sphk_ctx* ctx, const sphk_scene* s, const float* pos_last, float dt);
+/* XSPHViscosity_CUDA, PBDSolver.cu:89-125; Jacobi (the reference updates in place and races, Q5) */
+int sphk_pbd_xsph(sphk_ctx* ctx, const sphk_scene* s, float c, float rho0);
+
+/* ---- introspection for parity tests --------------------------------------------------------- */
+/* copies the stable-sort permutation of the last fluid search (perm[s] = pre-sort index) to device
+ * memory `perm_out` (int[n]) */
+int sphk_get_permutation(sphk_ctx* ctx, int* perm_out, int n);
+/* neighbour-list statistics of the last build: host ints {max_count, overflow_particles, total} */
+int sphk_list_stats(sphk_ctx* ctx, const sphk_scene* s, long long out_host[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHK_H_ */
