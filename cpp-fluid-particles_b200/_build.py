@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
+FACADE = os.path.join(HERE, "facade")
 INC = os.path.join(ROOT, "include")
 NVCC = os.environ.get("SPHK_NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = "/usr/bin/g++"
@@ -60,12 +61,15 @@ def build_sphk(force: bool = False, verbose_ptxas: bool = False) -> str:
             raise RuntimeError("nvcc failed")
         if verbose_ptxas:
             sys.stderr.write(out)
-    _run([NVCC, "-shared", "-o", LIBSPHK] + objs + ["-lcudart"])
+    _run([NVCC, "-shared", "-o", LIBSPHK] + objs + ["-lcudart", "-Xlinker", "-rpath=" + CUDA_LIB])
     return LIBSPHK
 
 
 def build_host(force: bool = False) -> str:
     srcs = sorted(os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".cpp"))
+    # the facade lives in its own directory so that its `#include "SPHSystem.h"` is resolved through -I
+    # (this repo's headers here, the reference's in oracle/ref_build) and never through the source directory
+    srcs += sorted(os.path.join(FACADE, f) for f in os.listdir(FACADE) if f.endswith(".cpp"))
     deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".h", ".hpp"))] + \
         [os.path.join(INC, "sphk.h"), os.path.join(INC, "sph_app.h"), LIBSPHK]
     if not force and _newer(LIBHOST, deps):

@@ -50,7 +50,7 @@ k_gather(const int* __restrict__ idxSorted, const float4* __restrict__ snapPos,
     if (vel) {
         const float4 v = snapVel[src];
         store3(vel, s, xyz(v));
-        vel4[s] = v;
+        if (vel4) vel4[s] = v;      // the boundary set has no velocity shadow
     }
 }
 

@@ -1,7 +1,7 @@
 /* sph_app.h -- headless C facade over the reference-shaped C++ class API
  * (SPHSystem / BaseSolver / SPHParticles / DArray).
  *
- * The facade source (cpp-fluid-particles_b200/host/sph_app.cpp) restates the ONLY call sites of
+ * The facade source (cpp-fluid-particles_b200/facade/sph_app.cpp) restates the ONLY call sites of
  * that API in the reference -- initSPHSystem() /root/reference/src/main.cpp:117-134 (particle
  * upload, solver choice, 16-argument SPHSystem constructor) and oneStep() main.cpp:300-306
  * (`float ms = pSystem->step()`) -- without GLUT/OpenGL.  The very same source file is compiled

@@ -1,0 +1,72 @@
+"""CPU-side checks of the boundary: the C-ABI libraries load and export every symbol the headers
+declare; without a GPU the product fails loudly (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from util import ROOT
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(sphk_[a-z_0-9]+|sph_app_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_sphk_exports_every_declared_symbol(pkg, built):
+    from cpp_fluid_particles_b200 import capi
+    L = capi.sphk()
+    names = _declared("sphk.h")
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(capi.SPHK_FUNCTIONS) == names, "capi.SPHK_FUNCTIONS out of sync with include/sphk.h"
+
+
+def test_host_facade_exports_every_declared_symbol(pkg, built):
+    from cpp_fluid_particles_b200 import capi
+    L = capi.app_lib()
+    names = [n for n in _declared("sph_app.h") if n != "sph_app_params"]
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.sph_app_engine() == b"b200-native"
+
+
+def test_reference_facade_is_the_same_source(built):
+    """The drop-in claim: ONE facade source, compiled against either header set."""
+    mk = open(os.path.join(ROOT, "oracle", "ref_build", "Makefile")).read()
+    assert "cpp-fluid-particles_b200/facade/sph_app.cpp" in mk
+    src = open(os.path.join(ROOT, "cpp-fluid-particles_b200", "facade", "sph_app.cpp")).read()
+    for inc in ("DArray.h", "Particles.h", "SPHParticles.h", "BaseSolver.h", "BasicSPHSolver.h", "DFSPHSolver.h",
+                "PBDSolver.h", "SPHSystem.h"):
+        assert f'#include "{inc}"' in src       # the reference's own include names (main.cpp:26-33)
+
+
+def test_no_device_fails_loudly(pkg, built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cpp_fluid_particles_b200 import capi
+    L = capi.sphk()
+    ctx = C.c_void_p()
+    g = capi.SphkGrid(); g.cell_size[:] = [4, 4, 4]; g.cell_length = 0.1
+    rc = L.sphk_create(C.byref(ctx), 8, 8, C.byref(g), None)
+    assert rc == -2 and not ctx.value
+    assert b"no CPU path" in L.sphk_error_string(rc)
+    with pytest.raises(RuntimeError):
+        capi.SphApp(pkg.scene.make_scene("mini"))
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under the package, include/ or pkgload may reference it."""
+    bad = []
+    for base in ("cpp-fluid-particles_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            for f in fs:
+                if f.endswith((".py", ".cpp", ".hpp", ".h", ".cu", ".cuh")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"(from|import)\s+oracle|liboracle|oracle/sph_oracle", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -194,8 +194,9 @@ def test_full_size_properties_2m(pkg, built):
     ps, _, _, csm, _ = O.neighbor_search(mini.fluid, np.zeros_like(mini.fluid), g)
     pb, _, _, csb, _ = O.neighbor_search(mini.boundary, None, g)
     A = O.SceneArrays(ps, np.full(ps.shape[0], mini.params.m0, np.float32), csm, pb, np.zeros(pb.shape[0], np.float32), csb, g, mini.params.radius)
-    interior = float(np.max(O.density(A)))
-    assert abs(float(np.max(dens)) - interior) <= 1e-5 * interior
+    ref_d = O.density(A)
+    interior = float(np.median(ref_d[ref_d > 0.99 * ref_d.max()]))
+    assert abs(float(np.median(dens[dens > 0.99 * dens.max()])) - interior) <= 1e-5 * interior
     stats = s.list_stats()
     assert stats["overflow"] == 0
     # idempotence: searching again on sorted input is the identity permutation
