@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the SPHSystem::step() hot path on a synthetic dam-break.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dfsph|wcsph|pbd] [--impl reference]
+
+A "step" is one SPHSystem::step(): neighbour search + one solver step over the whole particle set.
+Default workload at N=1: BASELINE.json configs[2], the configuration the north-star target is quoted on
+(2M-particle DFSPH dam-break, dt=0.004, exactly 4 divergence + 4 density iterations).  --workload wcsph /
+pbd select configs[1] / configs[3] on the same 2M scene.  N>1: x-slab decomposition, 2M particles per GPU
+(weak scaling; N=8 is BASELINE configs[4], the 16M scene), see cpp-fluid-particles_b200/slabs.py.
+
+Printed JSON (one line, rank 0):
+  value       whole-job particle-steps/s, state resident in HBM, timed on the device with CUDA events over
+              exactly K steps (barrier + synchronize on both sides, max over ranks)
+  e2e         the same metric through the reference-facing C++ class API (SPHSystem via the sph_app facade)
+              with HOST buffers: every step uploads pos+vel from pinned host memory, steps, and reads
+              pos+vel+density back; host<->device copies inside the timed region
+  roofline    the density kernel named by BASELINE.json's metric (for DFSPH: computeDensityAlpha's
+              replacement), timed live with CUDA events inside the timed region; algorithmic bytes per
+              particle from SURVEY.md 8(d); peak from MEASURED_PEAKS.json; `kernels` lists every sweep timed
+  cpu_baseline  the CPU restatement (oracle/, OpenMP, all host cores) on a bounded sample of the workload
+  clocks      nvidia-smi samples taken during the timed region
+--impl reference: the UNMODIFIED reference CUDA sources compiled for sm_100 (oracle/_ref/libsphref.so),
+driven through the very same facade source -- the "reference build" of the north star -- on the same
+scene; if that library is absent, the CPU restatement is timed instead (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES = {  # algorithmic HBM bytes per fluid particle per kernel invocation
+    "density": 20, "density_alpha": 24, "pressure_force": 48, "viscosity": 40, "color_grad": 28, "surface": 52,
+    "advect": 48, "dfsph_error": 44, "dfsph_correct": 44, "pbd_lambda": 24, "pbd_delta_pos": 32, "pbd_xsph": 40,
+    "neighbor_search": 126,
+}
+SCENE_OF_N = {1: "2m", 2: "4m", 4: "8m", 8: "16m"}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(pkg, solver: str, budget_s: float = 25.0) -> dict:
+    """The CPU restatement on a bounded sample of the workload: the same generator / constants / solver
+    settings at the largest scene whose constructor (= step 0) + 1 step fit the budget."""
+    from oracle import oracle as O
+    cores = O.num_threads()
+    best = None
+    for name in ("config0", "200k", "2m"):
+        sc = pkg.scene.benchmark_scene(name, solver)
+        n = sc.fluid.shape[0]
+        if best is not None and best["per_particle_s"] * n * 2.2 > budget_s:
+            break
+        s = O.OracleSystem(sc)        # includes step 0 (Q3)
+        t0 = time.perf_counter()
+        steps = 0
+        while steps < 1 or (time.perf_counter() - t0 < 1.0 and steps < 20):
+            s.step(); steps += 1
+        dt = (time.perf_counter() - t0) / steps
+        s.close()
+        best = {"value": n / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                "sample": f"{steps} step(s) of the {name} {solver} dam-break ({n} fluid particles), {dt*1e3:.1f} ms/step, "
+                          f"OpenMP over particles, gcc -O3", "per_particle_s": dt / n}
+    best.pop("per_particle_s", None)
+    return best
+
+
+def run_reference(args, pkg) -> dict:
+    import torch
+    from cpp_fluid_particles_b200 import capi
+    solver = args.workload
+    libref = os.path.join(ROOT, "oracle", "_ref", "libsphref.so")
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return {}
+    scene_name = args.scene or SCENE_OF_N.get(args.gpus, "2m")
+    if not (os.path.exists(libref) and torch.cuda.is_available()):
+        cb = cpu_baseline(pkg, solver, budget_s=60.0)
+        return {"impl": "reference", "metric": "particle-steps/sec (dam-break)", "value": cb["value"], "unit": cb["unit"],
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0,
+                                            "d2h_bytes_per_step": 0},
+                "config": {"workload": f"{solver} dam-break, CPU restatement (reference CUDA build unavailable here)"}}
+    if scene_name not in ("2m",):
+        scene_name = "2m"     # the reference is single-GPU: its arm always runs the 1-GPU scene
+    sc = pkg.scene.benchmark_scene(scene_name, solver)
+    n = sc.fluid.shape[0]
+    app = capi.SphApp(sc, libref)
+    for _ in range(args.warmup):
+        app.step()
+    sampler = ClockSampler(0); sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ms_self = [app.step() for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    app.close()
+    cb = cpu_baseline(pkg, solver)
+    value = n / dt
+    return {"impl": "reference", "metric": "particle-steps/sec (dam-break)", "value": value, "unit": "particle-steps/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "ms_per_step_self_reported": float(np.median(ms_self)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(scene_name, solver), "engine": "unmodified reference .cu files, nvcc "
+                       "-arch=sm_100 --expt-extended-lambda -use_fast_math, on the same B200 (the reference has no CPU path)"},
+            "cpu_baseline": {**cb, "note": "CPU restatement; the reference arm's own value is the reference CUDA build",
+                             "kind_of_value": "reference"},
+            "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "clocks": clocks}
+
+
+def workload_name(scene_name: str, solver: str) -> str:
+    desc = {"dfsph": "DFSPH dt=0.004, 4 divergence + 4 density iterations", "wcsph": "WCSPH dt=0.001",
+            "pbd": "PBD dt=0.004, 4 Jacobi projection iterations + XSPH"}[solver]
+    return f"{scene_name} dam-break, {desc}"
+
+
+def timed_kernels(solver: str):
+    """(label, method name on SphkSystem, algorithmic bytes key) of the sweeps timed individually."""
+    if solver == "dfsph":
+        return [("density_alpha", "dfsph_density_alpha", "density_alpha"), ("dfsph_div_error", "dfsph_div_error", "dfsph_error"),
+                ("dfsph_div_correct", "dfsph_div_correct", "dfsph_correct")]
+    if solver == "pbd":
+        return [("pbd_density_lambda", "pbd_density_lambda", "pbd_lambda"), ("pbd_delta_pos_apply", "pbd_delta_pos_apply", "pbd_delta_pos")]
+    return [("density", "density", "density"), ("pressure_force", "pressure_force", "pressure_force")]
+
+
+def run_ours_single(args, pkg) -> dict:
+    import torch
+    from cpp_fluid_particles_b200 import capi, engine
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: this engine has no CPU fallback"
+    solver = args.workload
+    scene_name = args.scene or "2m"
+    sc = pkg.scene.benchmark_scene(scene_name, solver)
+    n = sc.fluid.shape[0]
+    dev = torch.device("cuda:0")
+    # ---------------- device-resident value: python mirror = the same C-ABI calls as the C++ classes ----------
+    s = engine.SphkSystem(sc, device=dev)
+    ktimes = {}
+    evs = {}
+    hooks = timed_kernels(solver)
+
+    def wrap(label, meth):
+        inner = getattr(s, meth)
+        evs[label] = []
+
+        def timed(*a, **k):
+            if s._timing and len(evs[label]) < 2 * args.steps * 12:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); r = inner(*a, **k); e1.record()
+                evs[label].append((e0, e1))
+                return r
+            return inner(*a, **k)
+        setattr(s, meth, timed)
+
+    s._timing = False
+    for label, meth, _ in hooks:
+        wrap(label, meth)
+    search_evs = []
+    inner_search = s.search_fluid
+
+    def timed_search():
+        if s._timing:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); inner_search(); e1.record(); search_evs.append((e0, e1))
+        else:
+            inner_search()
+    s.search_fluid = timed_search
+    for _ in range(args.warmup):
+        s.step()
+    launches0 = s.launch_count()
+    sampler = ClockSampler(0); sampler.start()
+    s._timing = True
+    torch.cuda.synchronize()
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for _ in range(args.steps):
+        s.step()
+    e_stop.record()
+    torch.cuda.synchronize()
+    s._timing = False
+    ms_total = e_start.elapsed_time(e_stop)
+    clocks = sampler.stop()
+    launches = s.launch_count() - launches0
+    ms_step = ms_total / args.steps
+    value = n / (ms_step * 1e-3)
+    peak, peak_src = peaks()
+    kernels = []
+    for label, _, key in hooks:
+        t = [a.elapsed_time(b) for a, b in evs[label]]
+        if not t:
+            continue
+        ms = float(np.mean(t))
+        gbs = n * ALG_BYTES[key] / (ms * 1e-3) / 1e9
+        kernels.append({"kernel": label, "launches_timed": len(t), "ms": ms, "alg_bytes_per_particle": ALG_BYTES[key],
+                        "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": ms * len(t) / args.steps / ms_step})
+    t = [a.elapsed_time(b) for a, b in search_evs]
+    ms = float(np.mean(t))
+    gbs = n * ALG_BYTES["neighbor_search"] / (ms * 1e-3) / 1e9
+    kernels.append({"kernel": "neighbor_search (hash+sort+gather+ranges)", "launches_timed": len(t), "ms": ms,
+                    "alg_bytes_per_particle": ALG_BYTES["neighbor_search"], "achieved_gbs": gbs, "frac": gbs / peak,
+                    "share_of_step": ms / ms_step})
+    dens = kernels[0]
+    stats = s.list_stats() if solver != "pbd" else None
+    roof = {"bound": "hbm", "kernel": dens["kernel"], "achieved": dens["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": dens["frac"], "traffic": None, "peak_source": peak_src,
+            "alg_bytes_per_launch": n * dens["alg_bytes_per_particle"], "ms_per_launch": dens["ms"], "kernels": kernels,
+            "note": "neighbour sweeps are bound by FP32 issue / L1 gather rate, not HBM (SURVEY 8d): see DESIGN.md"}
+    if stats:
+        roof["neighbors_per_particle"] = stats["total"] / n
+    s.close()
+    del s
+    torch.cuda.empty_cache()
+    # ---------------- e2e: C++ class layer through the facade, host buffers ----------------------------------
+    app = capi.SphApp(sc)
+    pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()  # noqa: E731
+    hpos, hvel, hden = pin((n, 3)), pin((n, 3)), pin((n,))
+    app.download_into(hpos, hvel, hden)
+    for _ in range(max(1, args.warmup // 2)):
+        app.upload(hpos, hvel); app.step(); app.download_into(hpos, hvel, hden)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        app.upload(hpos, hvel)          # H2D: this step's inputs, from pinned host memory
+        app.step()                      # SPHSystem::step()
+        app.download_into(hpos, hvel, hden)   # D2H: the step's result
+    torch.cuda.synchronize()
+    e2e_dt = (time.perf_counter() - t0) / args.steps
+    assert np.isfinite(hden).all()
+    app.close()
+    e2e = {"value": n / e2e_dt, "unit": "particle-steps/s", "ms_per_step": e2e_dt * 1e3, "h2d_bytes_per_step": 24 * n,
+           "d2h_bytes_per_step": 28 * n, "api": "SPHSystem (C++ class layer) via sph_app facade; cudaMemcpy from/to pinned host buffers",
+           "timer": "host wall clock between device synchronisations (copies are host-synchronous)"}
+    cb = cpu_baseline(pkg, solver)
+    return {"metric": "particle-steps/sec (dam-break)", "value": value, "unit": "particle-steps/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(scene_name, solver), "n_fluid": n, "n_boundary": int(sc.boundary.shape[0]),
+                       "cells": list(sc.params.cell_size), "l2": "inputs larger than L2: packed particles + neighbour list "
+                       "working set per sweep is ~%d MB > 126 MB L2; no flush between steps" % int(n * (32 + 36 * 4) / 1e6),
+                       "parallelism": "1 GPU"},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "clocks": clocks}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="dfsph", choices=["dfsph", "wcsph", "pbd"])
+    ap.add_argument("--scene", default=None, help="override the scene (mini, config0, 200k, 2m, ...)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    import pkgload
+    pkg = pkgload.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        out = run_reference(args, pkg)
+        if out:
+            print(json.dumps(out), flush=True)
+        return
+    if world > 1 or args.gpus > 1:
+        from cpp_fluid_particles_b200 import slabs
+        out = slabs.bench_main(args, pkg)
+        if out:
+            print(json.dumps(out), flush=True)
+        return
+    print(json.dumps(run_ours_single(args, pkg)), flush=True)
+
+
+if __name__ == "__main__":
+    main()

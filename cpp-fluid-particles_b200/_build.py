@@ -75,7 +75,7 @@ def build_host(force: bool = False) -> str:
     if not force and _newer(LIBHOST, deps):
         return LIBHOST
     _run([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-I" + INC, "-I" + HOST, "-I" + CUDA_INC, "-o", LIBHOST]
-         + srcs + ["-L" + HERE, "-lsphk", "-L" + CUDA_LIB, "-lcudart", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + CUDA_LIB])
+         + srcs + ["-L" + HERE, "-lsphk", "-L" + CUDA_LIB, "-lcudart", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + CUDA_LIB, "-Wl,-Bsymbolic"])
     return LIBHOST
 
 

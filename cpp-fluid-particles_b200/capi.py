@@ -64,7 +64,9 @@ def _load(path: str):
     if not os.path.exists(path):
         raise RuntimeError(f"{os.path.basename(path)} is not built ({path}); run __graft_entry__.build() -- "
                            "this package has no CPU or pure-python fallback")
-    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+    # RTLD_LOCAL: libsphhost.so and the reference build oracle/_ref/libsphref.so export the SAME C++ class
+    # symbols (SPHSystem::step, ...) by design; they must never interpose each other in one process
+    return C.CDLL(path, mode=C.RTLD_LOCAL)
 
 
 def sphk():
