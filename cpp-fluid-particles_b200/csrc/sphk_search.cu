@@ -187,7 +187,7 @@ extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
     switch (option) {
     case SPHK_OPT_NEIGHBOR_LIST: c->useList = value != 0; return SPHK_OK;
     case SPHK_OPT_LIST_CAPACITY:
-        if (value < 8 || value > 1024) return SPHK_ERR_INVALID;
+        if (value < 8 || value > 1024 || (value & 3)) return SPHK_ERR_INVALID;   // multiple of 4 (int4 batches)
         if (value != c->kmax) {
             if (c->nbr) { cudaStreamSynchronize(c->stream); cudaFree(c->nbr); c->nbr = nullptr; }
             c->kmax = value; c->listEpoch = ~0ull;

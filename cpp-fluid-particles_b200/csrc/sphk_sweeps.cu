@@ -26,8 +26,10 @@ struct OpDensity {
     float* density;
     static constexpr bool kFluidOnly = false, kSplitB = false;
     struct Acc { float rho; };
+    struct Nb {};
+    __device__ Nb fetch(int, bool) const { return Nb{}; }
     __device__ void begin(Acc& a, int, float4, const DevScene&) const { a.rho = 0.f; }
-    template <bool B> __device__ void pair(Acc& a, int, int, float3, float r2, float4 pj, const DevScene& s) const {
+    template <bool B> __device__ void pair(Acc& a, int, int, float3, float r2, float4 pj, Nb, const DevScene& s) const {
         a.rho += pj.w * w_cubic(sqrtf(r2), s.R);
     }
     __device__ void end(Acc& a, int i, float4, const DevScene&) const { density[i] = a.rho; }
@@ -41,10 +43,12 @@ struct OpPressureForce {
     const float* prho; float4* vel4; float* vel; float dt;
     static constexpr bool kFluidOnly = false, kSplitB = true;
     struct Acc { float3 a; float pri; };
+    struct Nb { float prj; };
+    __device__ Nb fetch(int j, bool isB) const { return Nb{isB ? 0.f : prho[j]}; }
     __device__ void begin(Acc& a, int i, float4, const DevScene&) const { a.a = f3(0, 0, 0); a.pri = prho[i]; }
-    template <bool B> __device__ void pair(Acc& a, int i, int j, float3 d, float r2, float4 pj, const DevScene& s) const {
+    template <bool B> __device__ void pair(Acc& a, int i, int j, float3 d, float r2, float4 pj, Nb nb, const DevScene& s) const {
         if (B) a.a += -pj.w * a.pri * grad_w_cubic(d, sqrtf(r2), s.R);
-        else if (i != j) a.a += -pj.w * (a.pri + prho[j]) * grad_w_cubic(d, sqrtf(r2), s.R);
+        else if (i != j) a.a += -pj.w * (a.pri + nb.prj) * grad_w_cubic(d, sqrtf(r2), s.R);
     }
     __device__ void end(Acc& a, int i, float4, const DevScene&) const {
         float3 acc = a.a;
@@ -61,9 +65,11 @@ struct OpViscosity {
     const float4* vel4_in; float4* vel4_out; float* vel; float* deltaV; float rho0, visc, dt;
     static constexpr bool kFluidOnly = true, kSplitB = false;
     struct Acc { float3 a; float3 vi; };
+    struct Nb { float4 v; };
+    __device__ Nb fetch(int j, bool isB) const { return Nb{isB ? make_float4(0, 0, 0, 0) : vel4_in[j]}; }
     __device__ void begin(Acc& a, int i, float4, const DevScene&) const { a.a = f3(0, 0, 0); a.vi = xyz(vel4_in[i]); }
-    template <bool B> __device__ void pair(Acc& a, int, int j, float3, float r2, float4 pj, const DevScene& s) const {
-        const float3 vj = xyz(vel4_in[j]);
+    template <bool B> __device__ void pair(Acc& a, int, int, float3, float r2, float4 pj, Nb nb, const DevScene& s) const {
+        const float3 vj = xyz(nb.v);
         a.a += pj.w * ((vj - a.vi) / rho0) * lap_visc(sqrtf(r2), s.R);
     }
     __device__ void end(Acc& a, int i, float4, const DevScene&) const {
@@ -79,8 +85,10 @@ struct OpColorGrad {
     float* colorGrad; float rho0, rhoB;
     static constexpr bool kFluidOnly = false, kSplitB = true;
     struct Acc { float3 num; float den; };
+    struct Nb {};
+    __device__ Nb fetch(int, bool) const { return Nb{}; }
     __device__ void begin(Acc& a, int, float4, const DevScene&) const { a.num = f3(0, 0, 0); a.den = 0.f; }
-    template <bool B> __device__ void pair(Acc& a, int, int, float3 d, float r2, float4 pj, const DevScene& s) const {
+    template <bool B> __device__ void pair(Acc& a, int, int, float3 d, float r2, float4 pj, Nb, const DevScene& s) const {
         const float r = sqrtf(r2);
         const float V = pj.w / (B ? rhoB : rho0);
         a.num += V * grad_w_cubic(d, r, s.R);
@@ -99,9 +107,11 @@ struct OpSurface {
         const float3 ci = load3(colorGrad, i);
         a.cii = dot3(ci, ci); a.lci = sqrtf(a.cii);
     }
-    template <bool B> __device__ void pair(Acc& a, int, int j, float3 d, float r2, float4 pj, const DevScene& s) const {
+    struct Nb { float cjj; };
+    __device__ Nb fetch(int j, bool isB) const { return Nb{isB ? 0.f : cg2[j]}; }
+    template <bool B> __device__ void pair(Acc& a, int, int, float3 d, float r2, float4 pj, Nb nb, const DevScene& s) const {
         const float r = sqrtf(r2);
-        a.a += 0.25f * pj.w / (rho0 * rho0) * kappa * (a.cii + cg2[j]) * grad_surface_tension(d, r, s.R);
+        a.a += 0.25f * pj.w / (rho0 * rho0) * kappa * (a.cii + nb.cjj) * grad_surface_tension(d, r, s.R);
         a.a += airP * pj.w / (rho0 * rho0) * grad_w_cubic(d, r, s.R) * a.lci / fmaxf(SPHK_EPS, a.lci);
     }
     __device__ void end(Acc& a, int i, float4, const DevScene&) const {
@@ -116,8 +126,10 @@ struct OpDensityAlpha {
     float* density; float* alpha;
     static constexpr bool kFluidOnly = false, kSplitB = true;
     struct Acc { float den, lam; float3 gs; };
+    struct Nb {};
+    __device__ Nb fetch(int, bool) const { return Nb{}; }
     __device__ void begin(Acc& a, int, float4, const DevScene&) const { a.den = 0.f; a.lam = 0.f; a.gs = f3(0, 0, 0); }
-    template <bool B> __device__ void pair(Acc& a, int, int, float3 d, float r2, float4 pj, const DevScene& s) const {
+    template <bool B> __device__ void pair(Acc& a, int, int, float3 d, float r2, float4 pj, Nb, const DevScene& s) const {
         const float r = sqrtf(r2);
         a.den += pj.w * w_cubic(r, s.R);
         const float3 mg = pj.w * grad_w_cubic(d, r, s.R);
@@ -138,10 +150,12 @@ template <bool kDensity> struct OpDfsphError {
     static constexpr bool kFluidOnly = false, kSplitB = true;
     struct Acc { float e; float3 vi; };
     __device__ void begin(Acc& a, int i, float4, const DevScene&) const { a.e = 0.f; a.vi = xyz(vel4[i]); }
-    template <bool B> __device__ void pair(Acc& a, int, int j, float3 d, float r2, float4 pj, const DevScene& s) const {
+    struct Nb { float4 v; };
+    __device__ Nb fetch(int j, bool isB) const { return Nb{isB ? make_float4(0, 0, 0, 0) : vel4[j]}; }
+    template <bool B> __device__ void pair(Acc& a, int, int, float3 d, float r2, float4 pj, Nb nb, const DevScene& s) const {
         const float3 g = grad_w_cubic(d, sqrtf(r2), s.R);
         if (B) a.e += pj.w * dot3(a.vi, g);
-        else a.e += pj.w * dot3(a.vi - xyz(vel4[j]), g);
+        else a.e += pj.w * dot3(a.vi - xyz(nb.v), g);
     }
     __device__ void end(Acc& a, int i, float4, const DevScene&) const {
         float e;
@@ -164,10 +178,12 @@ template <int kMode /*0: vel += a, 1: vel += a/dt, 2: deltaPos = a/rho0*/> struc
     static constexpr bool kFluidOnly = false, kSplitB = true;
     struct Acc { float3 a; float ki; };
     __device__ void begin(Acc& a, int i, float4, const DevScene&) const { a.a = f3(0, 0, 0); a.ki = kappa[i]; }
-    template <bool B> __device__ void pair(Acc& a, int, int j, float3 d, float r2, float4 pj, const DevScene& s) const {
+    struct Nb { float kj; };
+    __device__ Nb fetch(int j, bool isB) const { return Nb{isB ? 0.f : kappa[j]}; }
+    template <bool B> __device__ void pair(Acc& a, int, int, float3 d, float r2, float4 pj, Nb nb, const DevScene& s) const {
         const float3 g = grad_w_cubic(d, sqrtf(r2), s.R);
         if (B) a.a += pj.w * a.ki * g;
-        else a.a += pj.w * (a.ki + kappa[j]) * g;
+        else a.a += pj.w * (a.ki + nb.kj) * g;
     }
     __device__ void end(Acc& a, int i, float4, const DevScene&) const {
         if (kMode == 2) { store3(deltaPos, i, a.a / dt_or_rho0); return; }
@@ -183,8 +199,10 @@ struct OpPbdLambda {
     float* density; float* lambda; float rho0, rho0AsBool, relaxation;
     static constexpr bool kFluidOnly = false, kSplitB = false;
     struct Acc { float den, lam; float3 gs; };
+    struct Nb {};
+    __device__ Nb fetch(int, bool) const { return Nb{}; }
     __device__ void begin(Acc& a, int, float4, const DevScene&) const { a.den = 0.f; a.lam = 0.f; a.gs = f3(0, 0, 0); }
-    template <bool B> __device__ void pair(Acc& a, int, int, float3 d, float r2, float4 pj, const DevScene& s) const {
+    template <bool B> __device__ void pair(Acc& a, int, int, float3 d, float r2, float4 pj, Nb, const DevScene& s) const {
         const float r = sqrtf(r2);
         a.den += pj.w * w_cubic(r, s.R);
         const float3 g = -pj.w * grad_w_cubic(d, r, s.R) / rho0AsBool;
@@ -204,8 +222,10 @@ struct OpXsph {
     static constexpr bool kFluidOnly = true, kSplitB = false;
     struct Acc { float3 a; float3 vi; };
     __device__ void begin(Acc& a, int i, float4, const DevScene&) const { a.a = f3(0, 0, 0); a.vi = xyz(vel4_in[i]); }
-    template <bool B> __device__ void pair(Acc& a, int, int j, float3, float r2, float4 pj, const DevScene& s) const {
-        a.a += pj.w * (xyz(vel4_in[j]) - a.vi) * w_cubic(sqrtf(r2), s.R);
+    struct Nb { float4 v; };
+    __device__ Nb fetch(int j, bool isB) const { return Nb{isB ? make_float4(0, 0, 0, 0) : vel4_in[j]}; }
+    template <bool B> __device__ void pair(Acc& a, int, int, float3, float r2, float4 pj, Nb nb, const DevScene& s) const {
+        a.a += pj.w * (xyz(nb.v) - a.vi) * w_cubic(sqrtf(r2), s.R);
     }
     __device__ void end(Acc& a, int i, float4, const DevScene&) const {
         const float3 v = a.vi + c * a.a / rho0;
@@ -219,13 +239,24 @@ struct OpBuildList {
     int* nbr; int* cnt;
     static constexpr bool kFluidOnly = false, kSplitB = false;
     struct Acc { int n; };
+    struct Nb {};
+    __device__ Nb fetch(int, bool) const { return Nb{}; }
     __device__ void begin(Acc& a, int, float4, const DevScene&) const { a.n = 0; }
-    template <bool B> __device__ void pair(Acc& a, int i, int j, float3, float, float4, const DevScene& s) const {
+    // layout: entries 4b..4b+3 of particle i form the int4 at nbr4[b * stride + i] (one coalesced LDG.128 per
+    // batch of four neighbours in the walk)
+    __device__ size_t slot(int n, int i, const DevScene& s) const {
+        return (static_cast<size_t>(n >> 2) * s.nbrStride + i) * 4 + (n & 3);
+    }
+    template <bool B> __device__ void pair(Acc& a, int i, int j, float3, float, float4, Nb, const DevScene& s) const {
         if (j == i) return;
-        if (a.n < s.kmax) nbr[static_cast<size_t>(a.n) * s.nbrStride + i] = j;
+        if (a.n < s.kmax) nbr[slot(a.n, i, s)] = j;
         ++a.n;
     }
-    __device__ void end(Acc& a, int i, float4, const DevScene&) const { cnt[i] = a.n; }
+    __device__ void end(Acc& a, int i, float4, const DevScene& s) const {
+        cnt[i] = a.n;
+        // pad the last batch with the particle itself: the self pair contributes exactly 0 to every operator
+        for (int n = a.n; (n & 3) && n < s.kmax; ++n) nbr[slot(n, i, s)] = i;
+    }
 };
 
 // =================================================================================================
@@ -245,7 +276,7 @@ __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, type
                 const float4 pj = s.posm[j];
                 const float3 d = xi - xyz(pj);
                 const float r2 = dot3(d, d);
-                if (r2 <= s.r2cut) op.template pair<false>(acc, i, j, d, r2, pj, s);
+                if (r2 <= s.r2cut) op.template pair<false>(acc, i, j, d, r2, pj, op.fetch(j, false), s);
             }
         }
         if (!Op::kFluidOnly) {
@@ -255,7 +286,7 @@ __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, type
                 const float4 pj = s.posm[j];
                 const float3 d = xi - xyz(pj);
                 const float r2 = dot3(d, d);
-                if (r2 <= s.r2cut) op.template pair<true>(acc, i, j, d, r2, pj, s);
+                if (r2 <= s.r2cut) op.template pair<true>(acc, i, j, d, r2, pj, op.fetch(j, true), s);
             }
         }
     }
@@ -273,6 +304,21 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_cells(const DevScene s, co
 }
 
 template <class Op>
+__device__ __forceinline__ void list_pair(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float3 xi, int j,
+                                          float4 pj, typename Op::Nb nb) {
+    const bool isB = j >= s.bOff;
+    if (Op::kFluidOnly && isB) return;
+    const float3 d = xi - xyz(pj);
+    const float r2 = dot3(d, d);
+    if (Op::kSplitB && isB) op.template pair<true>(acc, i, j, d, r2, pj, nb, s);
+    else op.template pair<false>(acc, i, j, d, r2, pj, nb, s);
+}
+
+// List walk, software-pipelined for memory-level parallelism: the four indices of a batch arrive in ONE
+// coalesced 16-byte load (streaming, evict-first: the list is read once per sweep and must not push the
+// gathered particle records out of L2), the next batch's indices are prefetched before the current batch
+// is consumed, and the 4 (+4 payload) dependent gathers of a batch are issued back to back before any math.
+template <class Op>
 __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, const Op op) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= s.nF) return;
@@ -282,16 +328,21 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, con
     op.begin(acc, i, pi, s);
     const int n = s.cnt[i];
     if (n <= s.kmax) {
-        const int* __restrict__ row = s.nbr + i;
-        for (int k = 0; k < n; ++k, row += s.nbrStride) {
-            const int j = *row;
-            const bool isB = j >= s.bOff;
-            if (Op::kFluidOnly && isB) continue;
-            const float4 pj = s.posm[j];
-            const float3 d = xi - xyz(pj);
-            const float r2 = dot3(d, d);
-            if (Op::kSplitB && isB) op.template pair<true>(acc, i, j, d, r2, pj, s);
-            else op.template pair<false>(acc, i, j, d, r2, pj, s);
+        const int nb4 = (n + 3) >> 2;
+        const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + i;
+        int4 jn = make_int4(i, i, i, i);
+        if (nb4 > 0) jn = __ldcs(row);
+        for (int b = 0; b < nb4; ++b) {
+            const int4 j4 = jn;
+            row += s.nbrStride;
+            if (b + 1 < nb4) jn = __ldcs(row);
+            const float4 p0 = __ldg(s.posm + j4.x), p1 = __ldg(s.posm + j4.y), p2 = __ldg(s.posm + j4.z), p3 = __ldg(s.posm + j4.w);
+            const typename Op::Nb n0 = op.fetch(j4.x, j4.x >= s.bOff), n1 = op.fetch(j4.y, j4.y >= s.bOff),
+                                  n2 = op.fetch(j4.z, j4.z >= s.bOff), n3 = op.fetch(j4.w, j4.w >= s.bOff);
+            list_pair(s, op, acc, i, xi, j4.x, p0, n0);
+            list_pair(s, op, acc, i, xi, j4.y, p1, n1);
+            list_pair(s, op, acc, i, xi, j4.z, p2, n2);
+            list_pair(s, op, acc, i, xi, j4.w, p3, n3);
         }
     } else {
         walk_cells(s, op, acc, i, pi);      // more neighbours than the list keeps: exact fallback
