@@ -9,6 +9,25 @@
 #define SPHK_MAX_A (1000.0f)                    // global.h:26
 #define SPHK_BLOCK 128
 
+// One particle = one 32-byte sector: a neighbour costs ONE 256-bit gather (LDG.E.256) in every sweep.
+//   x y z m : position + mass                      (rewritten by the neighbour search / advect / PBD apply)
+//   vx vy vz: velocity (0 for boundary particles)
+//   s       : the scalar the NEXT sweep reads from its neighbours: DFSPH stiffness kappa, PBD lambda,
+//             p/rho^2 (pressure force) or |colour gradient|^2 (surface tension); 0 for boundary particles
+struct __align__(32) Rec { float x, y, z, m, vx, vy, vz, s; };
+
+// per-launch constants of the smoothing kernels (CUDAFunctions.cuh:23-54,82-98), evaluated once on the host
+struct KConst {
+    float R;      // support radius
+    float hInv;   // 2 / R                 (q = r * hInv)
+    float cW;     // 0.25 / (pi R^3)
+    float cG;     // 1 / (pi R^5)
+    float cLap;   // 45 / (pi R^6)
+    float cST;    // 136.0241 / (pi R^9)
+    float stOff;  // 0.0156 R^6
+    float r2cut;  // R^2 (1 + 1e-5): candidates beyond contribute exactly 0
+};
+
 struct sphk_ctx {
     cudaStream_t stream = nullptr;
     int capF = 0, capB = 0;          // capacities; boundary lives at unified index capF + b
@@ -20,9 +39,8 @@ struct sphk_ctx {
     int *keys = nullptr, *keysSorted = nullptr, *idx = nullptr, *idxSorted = nullptr;
     void* cubTemp = nullptr; size_t cubTempBytes = 0;
     float4 *snapA = nullptr, *snapB = nullptr;   // [max(capF,capB)] snapshot / Jacobi temp
-    float4* posm = nullptr;                      // [capF + capB] xyz + mass, sorted order
-    float4* vel4 = nullptr;                      // [capF] xyz (+w unused), sorted order
-    float* aux = nullptr;                        // [capF + capB] per-sweep scalar (p/rho^2, |c|^2); boundary part 0
+    Rec* rec = nullptr;                          // [capF + capB] packed 32-byte particle records, sorted order
+    const void* sTag = nullptr;                  // which caller array rec[].s currently mirrors (nullptr: none)
     float* tmpF = nullptr;                       // [3*capF] permute temp
     float* partial = nullptr;                    // [1024] reduction partials
     int* nbr = nullptr;                          // [kmax * capF] neighbour list, nbr[k*capF + i]
@@ -40,14 +58,15 @@ struct sphk_ctx {
 };
 
 struct DevScene {
-    const float4* __restrict__ posm;
+    const Rec* rec;
     const int* __restrict__ csF;
     const int* __restrict__ csB;
     const int* __restrict__ nbr;
     const int* __restrict__ cnt;
     int nF, bOff, nbrStride, kmax;
     int3 cs;
-    float cellLength, R, r2cut;
+    float cellLength;
+    KConst k;
 };
 
 // ---- tiny float3 algebra (component-wise, left to right) ---------------------------------------
@@ -85,29 +104,49 @@ __device__ __forceinline__ int cell_index(int x, int y, int z, int3 cs) {
                                                                             : (cs.x * cs.y * cs.z);
 }
 
-// ---- smoothing kernels, CUDAFunctions.cuh:23-54,82-98 (r = |d| passed in where already known) ----
-__device__ __forceinline__ float w_cubic(float r, float R) {
-    const float q = 2.0f * fabsf(r) / R;
-    if (q > 2.0f || q < SPHK_EPS) return 0.0f;
-    const float a = 0.25f / (SPHK_PI * R * R * R);
-    return a * ((q > 1.0f) ? (2.0f - q) * (2.0f - q) * (2.0f - q) : ((3.0f * q - 6.0f) * q * q + 4.0f));
+// ---- record access --------------------------------------------------------------------------------
+__device__ __forceinline__ float4 rec_lo(const Rec* r) { return *reinterpret_cast<const float4*>(r); }
+__device__ __forceinline__ float4 rec_hi(const Rec* r) { return *(reinterpret_cast<const float4*>(r) + 1); }
+// one 256-bit load (SASS LDG.E.256): both halves of a record in a single L1 request
+__device__ __forceinline__ void rec_full(const Rec* r, float4& lo, float4& hi) {
+    asm("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+        : "l"(r));
 }
-__device__ __forceinline__ float3 grad_w_cubic(float3 d, float r, float R) {
-    const float q = 2.0f * r / R;
-    if (q > 2.0f) return f3(0.f, 0.f, 0.f);
-    const float3 a = d / (SPHK_PI * (q + SPHK_EPS) * R * R * R * R * R);
-    return a * ((q > 1.0f) ? ((12.0f - 3.0f * q) * q - 12.0f) : ((9.0f * q - 12.0f) * q));
+__device__ __forceinline__ void rec_set_pos(Rec* r, float3 p) {
+    *reinterpret_cast<float2*>(&r->x) = make_float2(p.x, p.y); r->z = p.z;
 }
-__device__ __forceinline__ float lap_visc(float r, float R) {
-    return (r <= R) ? (45.0f * (R - r) / (SPHK_PI * powf(R, 6))) : 0.0f;
+__device__ __forceinline__ void rec_set_vel(Rec* r, float3 v) {
+    *reinterpret_cast<float2*>(&r->vx) = make_float2(v.x, v.y); r->vz = v.z;
 }
-__device__ __forceinline__ float3 grad_surface_tension(float3 d, float x, float R) {
-    if (x > R || x < SPHK_EPS) return f3(0.f, 0.f, 0.f);
-    const float R3 = R * R * R;
-    const float3 a = 136.0241f * -d / (SPHK_PI * R3 * R3 * R3 * x);
-    const float e = R - x;
+
+// ---- smoothing kernels, CUDAFunctions.cuh:23-54,82-98 ------------------------------------------------
+// Same functions as the reference, arranged for the issue rate: constants folded per launch (KConst),
+// branch-free selects instead of early returns, one MUFU.RCP per gradient.  Differences from the
+// reference's expression order are a few ulp per term (<= ~3e-7 relative), far inside the 1e-5 budget.
+__device__ __forceinline__ float w_cubic(float r, const KConst& k) {
+    const float q = r * k.hInv;
+    const float t = 2.0f - q;
+    const float w = (q > 1.0f) ? t * t * t : ((3.0f * q - 6.0f) * q * q + 4.0f);
+    return (q > 2.0f || q < SPHK_EPS) ? 0.0f : k.cW * w;                   // W(0) = 0: quirk Q1
+}
+// scalar factor f with grad W = d * f
+__device__ __forceinline__ float grad_w_factor(float r, const KConst& k) {
+    const float q = r * k.hInv;
+    const float p = (q > 1.0f) ? ((12.0f - 3.0f * q) * q - 12.0f) : ((9.0f * q - 12.0f) * q);
+    const float f = __fdividef(k.cG, q + SPHK_EPS) * p;
+    return (q > 2.0f) ? 0.0f : f;
+}
+__device__ __forceinline__ float lap_visc(float r, const KConst& k) {
+    return (r <= k.R) ? k.cLap * (k.R - r) : 0.0f;
+}
+// scalar factor f with grad C = d * f (surface-tension kernel gradient; note the reference's -r)
+__device__ __forceinline__ float grad_st_factor(float x, const KConst& k) {
+    const float e = k.R - x;
     const float e3x3 = (e * e * e) * (x * x * x);
-    return a * ((2.0f * x <= R) ? (2.0f * e3x3 - 0.0156f * R3 * R3) : e3x3);
+    const float p = (2.0f * x <= k.R) ? (2.0f * e3x3 - k.stOff) : e3x3;
+    const float f = -__fdividef(k.cST, x) * p;
+    return (x > k.R || x < SPHK_EPS) ? 0.0f : f;
 }
 
 #define SPHK_CUDA_TRY(expr)                                  \

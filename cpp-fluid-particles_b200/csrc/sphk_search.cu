@@ -38,20 +38,22 @@ k_hash_snapshot(const float* __restrict__ pos, const float* __restrict__ vel, in
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_gather(const int* __restrict__ idxSorted, const float4* __restrict__ snapPos,
          const float4* __restrict__ snapVel, const float* __restrict__ mass, int n,
-         float* __restrict__ pos, float* __restrict__ vel, float4* __restrict__ posm,
-         float4* __restrict__ vel4) {
+         float* __restrict__ pos, float* __restrict__ vel, Rec* __restrict__ rec, int isFluid) {
     const int s = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (s >= n) return;
     const int src = idxSorted[s];
     float4 p = snapPos[src];
     store3(pos, s, xyz(p));
     p.w = mass[s];                      // mass is NOT permuted by the reference (Q2): slot s keeps mass[s]
-    posm[s] = p;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (vel) {
-        const float4 v = snapVel[src];
+        v = snapVel[src];
         store3(vel, s, xyz(v));
-        if (vel4) vel4[s] = v;      // the boundary set has no velocity shadow
+        if (!isFluid) v = make_float4(0.f, 0.f, 0.f, 0.f);   // boundary records carry zero velocity / scalar
     }
+    v.w = 0.f;
+    float4* out = reinterpret_cast<float4*>(rec + s);
+    out[0] = p; out[1] = v;
 }
 
 __global__ void __launch_bounds__(SPHK_BLOCK)
@@ -77,12 +79,15 @@ k_permute(const int* __restrict__ idxSorted, const float* __restrict__ src, floa
 
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_repack(const float* __restrict__ pos, const float* __restrict__ vel, const float* __restrict__ mass,
-         int n, float4* __restrict__ posm, float4* __restrict__ vel4) {
+         int n, Rec* __restrict__ rec) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= n) return;
     const float3 p = load3(pos, i);
-    posm[i] = make_float4(p.x, p.y, p.z, mass[i]);
-    if (vel) { const float3 v = load3(vel, i); vel4[i] = make_float4(v.x, v.y, v.z, 0.f); }
+    float4* out = reinterpret_cast<float4*>(rec + i);
+    out[0] = make_float4(p.x, p.y, p.z, mass[i]);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vel) { const float3 w = load3(vel, i); v = make_float4(w.x, w.y, w.z, 0.f); }
+    out[1] = v;
 }
 
 __global__ void __launch_bounds__(SPHK_BLOCK) k_fill(float* __restrict__ a, int n, float v) {
@@ -155,9 +160,7 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
     if (e == cudaSuccess) e = dalloc(&c->idxSorted, cap);
     if (e == cudaSuccess) e = dalloc(&c->snapA, cap);
     if (e == cudaSuccess) e = dalloc(&c->snapB, cap);
-    if (e == cudaSuccess) e = dalloc(&c->posm, tot);
-    if (e == cudaSuccess) e = dalloc(&c->vel4, static_cast<size_t>(max_fluid));
-    if (e == cudaSuccess) e = dalloc(&c->aux, tot);
+    if (e == cudaSuccess) e = dalloc(&c->rec, tot);
     if (e == cudaSuccess) e = dalloc(&c->tmpF, 3 * static_cast<size_t>(max_fluid));
     if (e == cudaSuccess) e = dalloc(&c->partial, 1024);
     if (e == cudaSuccess) e = dalloc(&c->cnt, static_cast<size_t>(max_fluid));
@@ -176,7 +179,7 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
 extern "C" void sphk_destroy(sphk_ctx* c) {
     if (!c) return;
     cudaFree(c->keys); cudaFree(c->keysSorted); cudaFree(c->idx); cudaFree(c->idxSorted);
-    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->posm); cudaFree(c->vel4); cudaFree(c->aux);
+    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec);
     cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
@@ -244,10 +247,10 @@ extern "C" int sphk_neighbor_search(sphk_ctx* c, int which, const sphk_particles
     SPHK_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cubTemp, tb, c->keys, c->keysSorted, c->idx, c->idxSorted, n, 0,
                                                   c->endBit, st));
     k_gather<<<sphk_blocks(n), SPHK_BLOCK, 0, st>>>(c->idxSorted, c->snapA, c->snapB, p->mass, n, p->pos, p->vel,
-                                                   c->posm + off, fluid ? c->vel4 : nullptr);
+                                                   c->rec + off, fluid ? 1 : 0);
     k_cell_start<<<sphk_blocks(c->ncells + 1), SPHK_BLOCK, 0, st>>>(c->keysSorted, n, c->ncells, cell_start);
     c->launches += 3 + 4;   // 3 own kernels + CUB onesweep (histogram, scan, <=3 passes): counted as 4
-    if (fluid) { c->nF = n; c->fluidSearched = true; c->permValid = true; c->searchEpoch++; c->posDirty = false; }
+    if (fluid) { c->nF = n; c->fluidSearched = true; c->permValid = true; c->searchEpoch++; c->posDirty = false; c->sTag = nullptr; }
     else { c->nB = n; c->boundarySearched = true; c->listEpoch = ~0ull; c->permValid = false; }
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;
@@ -256,6 +259,7 @@ extern "C" int sphk_neighbor_search(sphk_ctx* c, int which, const sphk_particles
 extern "C" int sphk_permute(sphk_ctx* c, float* array, int width, int n) {
     if (!c || !array || (width != 1 && width != 3)) return SPHK_ERR_INVALID;
     if (!c->permValid || n != c->nF) return SPHK_ERR_STATE;
+    if (array == c->sTag) c->sTag = nullptr;
     k_permute<<<sphk_blocks(n), SPHK_BLOCK, 0, c->stream>>>(c->idxSorted, array, c->tmpF, width, n);
     c->launches++;
     SPHK_CUDA_TRY(cudaMemcpyAsync(array, c->tmpF, sizeof(float) * static_cast<size_t>(n) * width,
@@ -266,13 +270,13 @@ extern "C" int sphk_permute(sphk_ctx* c, float* array, int width, int n) {
 extern "C" int sphk_refresh(sphk_ctx* c, const sphk_scene* s) {
     if (!c || !s) return SPHK_ERR_INVALID;
     if (!c->fluidSearched || s->fluid.n != c->nF) return SPHK_ERR_STATE;
-    k_repack<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(s->fluid.pos, s->fluid.vel, s->fluid.mass, c->nF,
-                                                              c->posm, c->vel4);
+    k_repack<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(s->fluid.pos, s->fluid.vel, s->fluid.mass, c->nF, c->rec);
     c->launches++;
     c->posDirty = true;
+    c->sTag = nullptr;
     if (c->boundarySearched && s->boundary.pos && s->boundary.n == c->nB) {
         k_repack<<<sphk_blocks(c->nB), SPHK_BLOCK, 0, c->stream>>>(s->boundary.pos, nullptr, s->boundary.mass, c->nB,
-                                                                  c->posm + c->capF, nullptr);
+                                                                  c->rec + c->capF);
         c->launches++;
     }
     SPHK_CUDA_TRY(cudaGetLastError());
@@ -282,6 +286,7 @@ extern "C" int sphk_refresh(sphk_ctx* c, const sphk_scene* s) {
 extern "C" int sphk_fill(sphk_ctx* c, float* array, int n, float value) {
     if (!c || !array || n < 0) return SPHK_ERR_INVALID;
     if (n == 0) return SPHK_OK;
+    if (array == c->sTag) c->sTag = nullptr;
     k_fill<<<sphk_blocks(n), SPHK_BLOCK, 0, c->stream>>>(array, n, value);
     c->launches++;
     // the fluid mass fill of SPHSystem.cu:73 happens after the first fluid search packed mass into the
@@ -292,6 +297,7 @@ extern "C" int sphk_fill(sphk_ctx* c, float* array, int n, float value) {
 
 extern "C" int sphk_copy(sphk_ctx* c, float* dst, const float* src, int n_floats) {
     if (!c || !dst || !src || n_floats < 0) return SPHK_ERR_INVALID;
+    if (dst == c->sTag) c->sTag = nullptr;
     SPHK_CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(float) * static_cast<size_t>(n_floats), cudaMemcpyDeviceToDevice, c->stream));
     return SPHK_OK;
 }
