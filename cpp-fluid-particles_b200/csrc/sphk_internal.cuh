@@ -10,11 +10,16 @@
 #define SPHK_BLOCK 128
 
 // One particle = one 32-byte sector: a neighbour costs ONE 256-bit gather (LDG.E.256) in every sweep.
-//   x y z m : position + mass                      (rewritten by the neighbour search / advect / PBD apply)
-//   vx vy vz: velocity (0 for boundary particles)
+//   x y z   : position                              (rewritten by the neighbour search / advect / PBD apply)
 //   s       : the scalar the NEXT sweep reads from its neighbours: DFSPH stiffness kappa, PBD lambda,
 //             p/rho^2 (pressure force) or |colour gradient|^2 (surface tension); 0 for boundary particles
-struct __align__(32) Rec { float x, y, z, m, vx, vy, vz, s; };
+//   vx vy vz: velocity (0 for boundary particles)
+//   m       : mass
+// Sweeps that need position + scalar gather only the first half (16 bytes); the mass of a fluid neighbour
+// is the uniform m0 when every fluid mass is equal (checked on the device at each neighbour search, always
+// true for the reference's scenes, SPHSystem.cu:73), else -- and for boundary neighbours -- it is read from
+// the second half.
+struct __align__(32) Rec { float x, y, z, s, vx, vy, vz, m; };
 
 // per-launch constants of the smoothing kernels (CUDAFunctions.cuh:23-54,82-98), evaluated once on the host
 struct KConst {
@@ -41,6 +46,7 @@ struct sphk_ctx {
     float4 *snapA = nullptr, *snapB = nullptr;   // [max(capF,capB)] snapshot / Jacobi temp
     Rec* rec = nullptr;                          // [capF + capB] packed 32-byte particle records, sorted order
     const void* sTag = nullptr;                  // which caller array rec[].s currently mirrors (nullptr: none)
+    float* massRange = nullptr;                  // [2] device: min / max fluid mass of the last search (as float bits)
     float* tmpF = nullptr;                       // [3*capF] permute temp
     float* partial = nullptr;                    // [1024] reduction partials
     int* nbr = nullptr;                          // [kmax * capF] neighbour list, nbr[k*capF + i]
@@ -63,6 +69,7 @@ struct DevScene {
     const int* __restrict__ csB;
     const int* __restrict__ nbr;
     const int* __restrict__ cnt;
+    const float* __restrict__ massRange;
     int nF, bOff, nbrStride, kmax;
     int3 cs;
     float cellLength;

@@ -38,22 +38,34 @@ k_hash_snapshot(const float* __restrict__ pos, const float* __restrict__ vel, in
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_gather(const int* __restrict__ idxSorted, const float4* __restrict__ snapPos,
          const float4* __restrict__ snapVel, const float* __restrict__ mass, int n,
-         float* __restrict__ pos, float* __restrict__ vel, Rec* __restrict__ rec, int isFluid) {
+         float* __restrict__ pos, float* __restrict__ vel, Rec* __restrict__ rec, int isFluid,
+         unsigned int* __restrict__ massRange) {
     const int s = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (s >= n) return;
-    const int src = idxSorted[s];
-    float4 p = snapPos[src];
-    store3(pos, s, xyz(p));
-    p.w = mass[s];                      // mass is NOT permuted by the reference (Q2): slot s keeps mass[s]
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (vel) {
-        v = snapVel[src];
-        store3(vel, s, xyz(v));
-        if (!isFluid) v = make_float4(0.f, 0.f, 0.f, 0.f);   // boundary records carry zero velocity / scalar
+    float m = 0.f;
+    if (s < n) {
+        const int src = idxSorted[s];
+        float4 p = snapPos[src];
+        store3(pos, s, xyz(p));
+        p.w = 0.f;                          // rec.s
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vel) {
+            v = snapVel[src];
+            store3(vel, s, xyz(v));
+            if (!isFluid) v = make_float4(0.f, 0.f, 0.f, 0.f);   // boundary records carry zero velocity / scalar
+        }
+        m = mass[s];                        // mass is NOT permuted by the reference (Q2): slot s keeps mass[s]
+        v.w = m;
+        float4* out = reinterpret_cast<float4*>(rec + s);
+        out[0] = p; out[1] = v;
     }
-    v.w = 0.f;
-    float4* out = reinterpret_cast<float4*>(rec + s);
-    out[0] = p; out[1] = v;
+    if (isFluid) {                          // min / max fluid mass (non-negative floats order like their bits)
+        float lo = (s < n) ? m : 3.0e38f, hi = (s < n) ? m : 0.f;
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(massRange, __float_as_uint(lo)); atomicMax(massRange + 1, __float_as_uint(hi)); }
+    }
 }
 
 __global__ void __launch_bounds__(SPHK_BLOCK)
@@ -79,16 +91,29 @@ k_permute(const int* __restrict__ idxSorted, const float* __restrict__ src, floa
 
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_repack(const float* __restrict__ pos, const float* __restrict__ vel, const float* __restrict__ mass,
-         int n, Rec* __restrict__ rec) {
+         int n, Rec* __restrict__ rec, unsigned int* __restrict__ massRange) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= n) return;
-    const float3 p = load3(pos, i);
-    float4* out = reinterpret_cast<float4*>(rec + i);
-    out[0] = make_float4(p.x, p.y, p.z, mass[i]);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (vel) { const float3 w = load3(vel, i); v = make_float4(w.x, w.y, w.z, 0.f); }
-    out[1] = v;
+    float m = 0.f;
+    if (i < n) {
+        const float3 p = load3(pos, i);
+        m = mass[i];
+        float4* out = reinterpret_cast<float4*>(rec + i);
+        out[0] = make_float4(p.x, p.y, p.z, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, m);
+        if (vel) { const float3 w = load3(vel, i); v = make_float4(w.x, w.y, w.z, m); }
+        out[1] = v;
+    }
+    if (massRange) {
+        float lo = (i < n) ? m : 3.0e38f, hi = (i < n) ? m : 0.f;
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(massRange, __float_as_uint(lo)); atomicMax(massRange + 1, __float_as_uint(hi)); }
+    }
 }
+
+__global__ void k_init_mass_range(unsigned int* r) { r[0] = 0x7f7fffffu; r[1] = 0u; }
 
 __global__ void __launch_bounds__(SPHK_BLOCK) k_fill(float* __restrict__ a, int n, float v) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
@@ -161,6 +186,7 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
     if (e == cudaSuccess) e = dalloc(&c->snapA, cap);
     if (e == cudaSuccess) e = dalloc(&c->snapB, cap);
     if (e == cudaSuccess) e = dalloc(&c->rec, tot);
+    if (e == cudaSuccess) e = dalloc(&c->massRange, 2);
     if (e == cudaSuccess) e = dalloc(&c->tmpF, 3 * static_cast<size_t>(max_fluid));
     if (e == cudaSuccess) e = dalloc(&c->partial, 1024);
     if (e == cudaSuccess) e = dalloc(&c->cnt, static_cast<size_t>(max_fluid));
@@ -179,7 +205,7 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
 extern "C" void sphk_destroy(sphk_ctx* c) {
     if (!c) return;
     cudaFree(c->keys); cudaFree(c->keysSorted); cudaFree(c->idx); cudaFree(c->idxSorted);
-    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec);
+    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec); cudaFree(c->massRange);
     cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
@@ -246,8 +272,9 @@ extern "C" int sphk_neighbor_search(sphk_ctx* c, int which, const sphk_particles
     size_t tb = c->cubTempBytes;
     SPHK_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cubTemp, tb, c->keys, c->keysSorted, c->idx, c->idxSorted, n, 0,
                                                   c->endBit, st));
+    if (fluid) k_init_mass_range<<<1, 1, 0, st>>>(reinterpret_cast<unsigned int*>(c->massRange));
     k_gather<<<sphk_blocks(n), SPHK_BLOCK, 0, st>>>(c->idxSorted, c->snapA, c->snapB, p->mass, n, p->pos, p->vel,
-                                                   c->rec + off, fluid ? 1 : 0);
+                                                   c->rec + off, fluid ? 1 : 0, reinterpret_cast<unsigned int*>(c->massRange));
     k_cell_start<<<sphk_blocks(c->ncells + 1), SPHK_BLOCK, 0, st>>>(c->keysSorted, n, c->ncells, cell_start);
     c->launches += 3 + 4;   // 3 own kernels + CUB onesweep (histogram, scan, <=3 passes): counted as 4
     if (fluid) { c->nF = n; c->fluidSearched = true; c->permValid = true; c->searchEpoch++; c->posDirty = false; c->sTag = nullptr; }
@@ -270,13 +297,15 @@ extern "C" int sphk_permute(sphk_ctx* c, float* array, int width, int n) {
 extern "C" int sphk_refresh(sphk_ctx* c, const sphk_scene* s) {
     if (!c || !s) return SPHK_ERR_INVALID;
     if (!c->fluidSearched || s->fluid.n != c->nF) return SPHK_ERR_STATE;
-    k_repack<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(s->fluid.pos, s->fluid.vel, s->fluid.mass, c->nF, c->rec);
+    k_init_mass_range<<<1, 1, 0, c->stream>>>(reinterpret_cast<unsigned int*>(c->massRange));
+    k_repack<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(s->fluid.pos, s->fluid.vel, s->fluid.mass, c->nF, c->rec,
+                                                              reinterpret_cast<unsigned int*>(c->massRange));
     c->launches++;
     c->posDirty = true;
     c->sTag = nullptr;
     if (c->boundarySearched && s->boundary.pos && s->boundary.n == c->nB) {
         k_repack<<<sphk_blocks(c->nB), SPHK_BLOCK, 0, c->stream>>>(s->boundary.pos, nullptr, s->boundary.mass, c->nB,
-                                                                  c->rec + c->capF);
+                                                                  c->rec + c->capF, nullptr);
         c->launches++;
     }
     SPHK_CUDA_TRY(cudaGetLastError());

@@ -23,10 +23,10 @@
 
 // =================================================================================================
 // Operators.  Acc = per-particle register accumulator.
-//   begin(acc, i, lo_i, hi_i)                 lo = {x,y,z,m}, hi = {vx,vy,vz,s} of particle i
-//   pair (acc, i, j, isB, d, r2, lo_j, hi_j)  d = x_i - x_j;  j is the unified index (boundary b = capF + b)
+//   begin(acc, i, lo_i, hi_i)                     lo = {x,y,z,s}, hi = {vx,vy,vz,m} of particle i
+//   pair (acc, i, j, isB, d, r2, mj, lo_j, hi_j)  d = x_i - x_j; mj = mass_j; j unified index (boundary b = capF + b)
 //   end  (acc, i, lo_i, hi_i)
-// kHi: the operator reads hi_j (velocity / scalar) of its neighbours -> 256-bit gather, else 128-bit.
+// kHi: the operator reads the velocity of its neighbours -> 256-bit gather; else 128-bit (position + scalar).
 // Boundary records carry v = 0 and s = 0, so "v_i - v_j", "kappa_i + kappa_j", "p_i/rho_i^2 + p_j/rho_j^2"
 // evaluate the reference's boundary terms without a separate code path (x - 0 and x + 0 are exact).
 // =================================================================================================
@@ -37,8 +37,8 @@ struct OpDensity {
     static constexpr bool kFluidOnly = false, kHi = false;
     struct Acc { float rho; };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.rho = 0.f; }
-    __device__ void pair(Acc& a, int, int, bool, float3, float r2, float4 lo, float4, const DevScene& s) const {
-        a.rho += lo.w * w_cubic(sqrtf(r2), s.k);
+    __device__ void pair(Acc& a, int, int, bool, float3, float r2, float mj, float4 lo, float4, const DevScene& s) const {
+        a.rho += mj * w_cubic(sqrtf(r2), s.k);
     }
     __device__ void end(Acc& a, int i, float4, float4, const DevScene&) const { density[i] = a.rho; }
 };
@@ -47,12 +47,12 @@ struct OpDensity {
 // (identical value to the reference's per-pair expression); the particle's own value comes from its record.
 struct OpPressureForce {
     Rec* rec; float* vel; float dt;
-    static constexpr bool kFluidOnly = false, kHi = true;
+    static constexpr bool kFluidOnly = false, kHi = false;
     struct Acc { float3 a; float pri; };
-    __device__ void begin(Acc& a, int, float4, float4 hi, const DevScene&) const { a.a = f3(0, 0, 0); a.pri = hi.w; }
-    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float4 lo, float4 hi, const DevScene& s) const {
+    __device__ void begin(Acc& a, int, float4 lo, float4, const DevScene&) const { a.a = f3(0, 0, 0); a.pri = lo.w; }
+    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
         // `i != j` of BasicSPHSolver.cu:120 is implied: the self pair has d = 0 and contributes 0
-        a.a += -lo.w * (a.pri + hi.w) * (d * grad_w_factor(sqrtf(r2), s.k));
+        a.a += -mj * (a.pri + lo.w) * (d * grad_w_factor(sqrtf(r2), s.k));
     }
     __device__ void end(Acc& a, int i, float4, float4 hi, const DevScene&) const {
         float3 acc = a.a;
@@ -69,8 +69,8 @@ struct OpViscosity {
     static constexpr bool kFluidOnly = true, kHi = true;
     struct Acc { float3 a; float3 vi; };
     __device__ void begin(Acc& a, int, float4, float4 hi, const DevScene&) const { a.a = f3(0, 0, 0); a.vi = xyz(hi); }
-    __device__ void pair(Acc& a, int, int, bool, float3, float r2, float4 lo, float4 hi, const DevScene& s) const {
-        a.a += lo.w * ((xyz(hi) - a.vi) / rho0) * lap_visc(sqrtf(r2), s.k);
+    __device__ void pair(Acc& a, int, int, bool, float3, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
+        a.a += mj * ((xyz(hi) - a.vi) / rho0) * lap_visc(sqrtf(r2), s.k);
     }
     __device__ void end(Acc& a, int i, float4, float4, const DevScene&) const {
         const float3 dv = visc * a.a * dt;
@@ -86,9 +86,9 @@ struct OpColorGrad {
     static constexpr bool kFluidOnly = false, kHi = false;
     struct Acc { float3 num; float den; };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.num = f3(0, 0, 0); a.den = 0.f; }
-    __device__ void pair(Acc& a, int, int, bool isB, float3 d, float r2, float4 lo, float4, const DevScene& s) const {
+    __device__ void pair(Acc& a, int, int, bool isB, float3 d, float r2, float mj, float4 lo, float4, const DevScene& s) const {
         const float r = sqrtf(r2);
-        const float V = lo.w / (isB ? rhoB : rho0);
+        const float V = mj / (isB ? rhoB : rho0);
         a.num += V * (d * grad_w_factor(r, s.k));
         a.den += V * w_cubic(r, s.k);
     }
@@ -98,18 +98,18 @@ struct OpColorGrad {
 // surfaceTensionAndAirPressure_CUDA, BasicSPHSolver.cu:332-370.  rec.s = dot(c, c) precomputed.
 struct OpSurface {
     Rec* rec; float* vel; float dt, rho0, kappa, airP;
-    static constexpr bool kFluidOnly = true, kHi = true;
+    static constexpr bool kFluidOnly = true, kHi = false;
     struct Acc { float3 a; float cii, ratio; };
-    __device__ void begin(Acc& a, int, float4, float4 hi, const DevScene&) const {
+    __device__ void begin(Acc& a, int, float4 lo, float4, const DevScene&) const {
         a.a = f3(0, 0, 0);
-        a.cii = hi.w;
-        const float lci = sqrtf(hi.w);
+        a.cii = lo.w;
+        const float lci = sqrtf(lo.w);
         a.ratio = lci / fmaxf(SPHK_EPS, lci);       // "disable inner particles", :349
     }
-    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float4 lo, float4 hi, const DevScene& s) const {
+    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
         const float r = sqrtf(r2);
-        const float mr = lo.w / (rho0 * rho0);
-        a.a += 0.25f * mr * kappa * (a.cii + hi.w) * (d * grad_st_factor(r, s.k));
+        const float mr = mj / (rho0 * rho0);
+        a.a += 0.25f * mr * kappa * (a.cii + lo.w) * (d * grad_st_factor(r, s.k));
         a.a += airP * mr * (d * grad_w_factor(r, s.k)) * a.ratio;
     }
     __device__ void end(Acc& a, int i, float4, float4 hi, const DevScene&) const {
@@ -124,10 +124,10 @@ struct OpDensityAlpha {
     static constexpr bool kFluidOnly = false, kHi = false;
     struct Acc { float den, lam; float3 gs; };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.den = 0.f; a.lam = 0.f; a.gs = f3(0, 0, 0); }
-    __device__ void pair(Acc& a, int, int, bool isB, float3 d, float r2, float4 lo, float4, const DevScene& s) const {
+    __device__ void pair(Acc& a, int, int, bool isB, float3 d, float r2, float mj, float4 lo, float4, const DevScene& s) const {
         const float r = sqrtf(r2);
-        a.den += lo.w * w_cubic(r, s.k);
-        const float3 mg = lo.w * (d * grad_w_factor(r, s.k));
+        a.den += mj * w_cubic(r, s.k);
+        const float3 mg = mj * (d * grad_w_factor(r, s.k));
         a.gs += mg;
         a.lam += isB ? 0.0f : dot3(mg, mg);         // boundary excluded from the second term, :218
     }
@@ -146,8 +146,8 @@ template <bool kDensity> struct OpDfsphError {
     static constexpr bool kFluidOnly = false, kHi = true;
     struct Acc { float e; float3 vi; };
     __device__ void begin(Acc& a, int, float4, float4 hi, const DevScene&) const { a.e = 0.f; a.vi = xyz(hi); }
-    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float4 lo, float4 hi, const DevScene& s) const {
-        a.e += lo.w * dot3(a.vi - xyz(hi), d * grad_w_factor(sqrtf(r2), s.k));
+    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
+        a.e += mj * dot3(a.vi - xyz(hi), d * grad_w_factor(sqrtf(r2), s.k));
     }
     __device__ void end(Acc& a, int i, float4, float4, const DevScene&) const {
         float e;
@@ -168,11 +168,11 @@ template <bool kDensity> struct OpDfsphError {
 // computeDeltaPos_CUDA (PBDSolver.cu:170-210) shares the pair term with lambda as the scalar.  Reads rec.s.
 template <int kMode /*0: vel += a, 1: vel += a/dt, 2: deltaPos = a/rho0*/> struct OpScalarGradient {
     Rec* rec; float* vel; float* deltaPos; float dt_or_rho0;
-    static constexpr bool kFluidOnly = false, kHi = true;
+    static constexpr bool kFluidOnly = false, kHi = false;
     struct Acc { float3 a; float ki; };
-    __device__ void begin(Acc& a, int, float4, float4 hi, const DevScene&) const { a.a = f3(0, 0, 0); a.ki = hi.w; }
-    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float4 lo, float4 hi, const DevScene& s) const {
-        a.a += lo.w * (a.ki + hi.w) * (d * grad_w_factor(sqrtf(r2), s.k));
+    __device__ void begin(Acc& a, int, float4 lo, float4, const DevScene&) const { a.a = f3(0, 0, 0); a.ki = lo.w; }
+    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
+        a.a += mj * (a.ki + lo.w) * (d * grad_w_factor(sqrtf(r2), s.k));
     }
     __device__ void end(Acc& a, int i, float4, float4 hi, const DevScene&) const {
         if (kMode == 2) { store3(deltaPos, i, a.a / dt_or_rho0); return; }
@@ -188,10 +188,10 @@ struct OpPbdLambda {
     static constexpr bool kFluidOnly = false, kHi = false;
     struct Acc { float den, lam; float3 gs; };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.den = 0.f; a.lam = 0.f; a.gs = f3(0, 0, 0); }
-    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float4 lo, float4, const DevScene& s) const {
+    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float mj, float4 lo, float4, const DevScene& s) const {
         const float r = sqrtf(r2);
-        a.den += lo.w * w_cubic(r, s.k);
-        const float3 g = -lo.w * (d * grad_w_factor(r, s.k)) / rho0AsBool;
+        a.den += mj * w_cubic(r, s.k);
+        const float3 g = -mj * (d * grad_w_factor(r, s.k)) / rho0AsBool;
         a.gs -= g;
         a.lam += dot3(g, g);
     }
@@ -210,8 +210,8 @@ struct OpXsph {
     static constexpr bool kFluidOnly = true, kHi = true;
     struct Acc { float3 a; float3 vi; };
     __device__ void begin(Acc& a, int, float4, float4 hi, const DevScene&) const { a.a = f3(0, 0, 0); a.vi = xyz(hi); }
-    __device__ void pair(Acc& a, int, int, bool, float3, float r2, float4 lo, float4 hi, const DevScene& s) const {
-        a.a += lo.w * (xyz(hi) - a.vi) * w_cubic(sqrtf(r2), s.k);
+    __device__ void pair(Acc& a, int, int, bool, float3, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
+        a.a += mj * (xyz(hi) - a.vi) * w_cubic(sqrtf(r2), s.k);
     }
     __device__ void end(Acc& a, int i, float4, float4, const DevScene&) const {
         const float3 v = a.vi + c * a.a / rho0;
@@ -231,7 +231,7 @@ struct OpBuildList {
     __device__ size_t slot(int n, int i, const DevScene& s) const {
         return (static_cast<size_t>(n >> 2) * s.nbrStride + i) * 4 + (n & 3);
     }
-    __device__ void pair(Acc& a, int i, int j, bool, float3, float, float4, float4, const DevScene& s) const {
+    __device__ void pair(Acc& a, int i, int j, bool, float3, float, float mj, float4, float4, const DevScene& s) const {
         if (j == i) return;
         if (a.n < s.kmax) nbr[slot(a.n, i, s)] = j;
         ++a.n;
@@ -251,9 +251,21 @@ __device__ __forceinline__ void fetch(const DevScene& s, int j, float4& lo, floa
     if (Op::kHi) rec_full(s.rec + j, lo, hi);
     else { lo = rec_lo(s.rec + j); hi = make_float4(0.f, 0.f, 0.f, 0.f); }
 }
+// mass of neighbour j: free when the second half was gathered; else the uniform fluid mass, or one extra
+// 4-byte load for boundary neighbours / non-uniform fluid masses
+template <class Op>
+__device__ __forceinline__ float mass_of(const DevScene& s, int j, bool isB, float4 hi, float m0) {
+    if (Op::kHi) return hi.w;
+    return (isB || m0 < 0.f) ? s.rec[j].m : m0;
+}
+// uniform fluid mass of the last search, or -1 when the masses differ
+__device__ __forceinline__ float uniform_mass(const DevScene& s) {
+    const float lo = s.massRange[0], hi = s.massRange[1];
+    return (lo == hi) ? lo : -1.0f;
+}
 
 template <class Op>
-__device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float4 pi) {
+__device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float4 pi, float m0) {
     const int cx = cell_coord(pi.x, s.cellLength), cy = cell_coord(pi.y, s.cellLength), cz = cell_coord(pi.z, s.cellLength);
     const float3 xi = xyz(pi);
 #pragma unroll 1
@@ -267,7 +279,7 @@ __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, type
                 fetch<Op>(s, j, lo, hi);
                 const float3 d = xi - xyz(lo);
                 const float r2 = dot3(d, d);
-                if (r2 <= s.k.r2cut) op.pair(acc, i, j, false, d, r2, lo, hi, s);
+                if (r2 <= s.k.r2cut) op.pair(acc, i, j, false, d, r2, mass_of<Op>(s, j, false, hi, m0), lo, hi, s);
             }
         }
         if (!Op::kFluidOnly) {
@@ -278,7 +290,7 @@ __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, type
                 fetch<Op>(s, j, lo, hi);
                 const float3 d = xi - xyz(lo);
                 const float r2 = dot3(d, d);
-                if (r2 <= s.k.r2cut) op.pair(acc, i, j, true, d, r2, lo, hi, s);
+                if (r2 <= s.k.r2cut) op.pair(acc, i, j, true, d, r2, mass_of<Op>(s, j, true, hi, m0), lo, hi, s);
             }
         }
     }
@@ -292,17 +304,17 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_cells(const DevScene s, co
     rec_full(s.rec + i, lo, hi);
     typename Op::Acc acc;
     op.begin(acc, i, lo, hi, s);
-    walk_cells(s, op, acc, i, lo);
+    walk_cells(s, op, acc, i, lo, uniform_mass(s));
     op.end(acc, i, lo, hi, s);
 }
 
 template <class Op>
 __device__ __forceinline__ void list_pair(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float3 xi, int j,
-                                          float4 lo, float4 hi) {
+                                          float4 lo, float4 hi, float m0) {
     const bool isB = j >= s.bOff;
     if (Op::kFluidOnly && isB) return;
     const float3 d = xi - xyz(lo);
-    op.pair(acc, i, j, isB, d, dot3(d, d), lo, hi, s);
+    op.pair(acc, i, j, isB, d, dot3(d, d), mass_of<Op>(s, j, isB, hi, m0), lo, hi, s);
 }
 
 template <class Op>
@@ -315,6 +327,7 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, con
     typename Op::Acc acc;
     op.begin(acc, i, lo, hi, s);
     const int n = s.cnt[i];
+    const float m0 = uniform_mass(s);
     if (n <= s.kmax) {
         const int nb4 = (n + 3) >> 2;
         const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + i;
@@ -326,13 +339,13 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, con
             if (b + 1 < nb4) jn = __ldcs(row);
             float4 l0, h0, l1, h1, l2, h2, l3, h3;
             fetch<Op>(s, j4.x, l0, h0); fetch<Op>(s, j4.y, l1, h1); fetch<Op>(s, j4.z, l2, h2); fetch<Op>(s, j4.w, l3, h3);
-            list_pair(s, op, acc, i, xi, j4.x, l0, h0);
-            list_pair(s, op, acc, i, xi, j4.y, l1, h1);
-            list_pair(s, op, acc, i, xi, j4.z, l2, h2);
-            list_pair(s, op, acc, i, xi, j4.w, l3, h3);
+            list_pair(s, op, acc, i, xi, j4.x, l0, h0, m0);
+            list_pair(s, op, acc, i, xi, j4.y, l1, h1, m0);
+            list_pair(s, op, acc, i, xi, j4.z, l2, h2, m0);
+            list_pair(s, op, acc, i, xi, j4.w, l3, h3, m0);
         }
     } else {
-        walk_cells(s, op, acc, i, lo);      // more neighbours than the list keeps: exact fallback
+        walk_cells(s, op, acc, i, lo, m0);  // more neighbours than the list keeps: exact fallback
     }
     op.end(acc, i, lo, hi, s);
 }
@@ -482,7 +495,7 @@ static KConst kernel_constants(float R) {
 static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
     DevScene d;
     d.rec = c->rec; d.csF = s->cell_start_fluid; d.csB = s->cell_start_boundary;
-    d.nbr = c->nbr; d.cnt = c->cnt;
+    d.nbr = c->nbr; d.cnt = c->cnt; d.massRange = c->massRange;
     d.nF = c->nF; d.bOff = c->capF; d.nbrStride = c->capF; d.kmax = c->kmax;
     d.cs = c->cs; d.cellLength = c->cellLength;
     d.k = kernel_constants(s->radius);
