@@ -24,7 +24,7 @@ SPHK_FUNCTIONS = [
     "sphk_pressure_force", "sphk_advect", "sphk_dfsph_density_alpha", "sphk_dfsph_div_error", "sphk_dfsph_div_correct",
     "sphk_dfsph_den_error", "sphk_dfsph_den_correct", "sphk_reduce_abs_sum", "sphk_copy", "sphk_pbd_density_lambda",
     "sphk_pbd_delta_pos_apply", "sphk_pbd_velocity_from_positions", "sphk_pbd_xsph", "sphk_get_permutation",
-    "sphk_list_stats",
+    "sphk_list_stats", "sphk_set_active_range", "sphk_push_range",
 ]
 SPH_APP_FUNCTIONS = [
     "sph_app_create", "sph_app_destroy", "sph_app_step", "sph_app_fluid_size", "sph_app_boundary_size",
@@ -35,7 +35,7 @@ OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_TILE_SWEEP = 1, 2, 3
 
 
 class SphkGrid(C.Structure):
-    _fields_ = [("cell_size", C.c_int * 3), ("cell_length", C.c_float)]
+    _fields_ = [("cell_size", C.c_int * 3), ("cell_length", C.c_float), ("origin", C.c_int * 3)]
 
 
 class SphkParticles(C.Structure):

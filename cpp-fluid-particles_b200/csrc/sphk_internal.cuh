@@ -37,6 +37,7 @@ struct sphk_ctx {
     cudaStream_t stream = nullptr;
     int capF = 0, capB = 0;          // capacities; boundary lives at unified index capF + b
     int3 cs = {0, 0, 0};
+    int3 org = {0, 0, 0};            // cell-coordinate origin of the local grid (slab ranks)
     int ncells = 0;
     float cellLength = 0.f;
     int endBit = 32;                 // radix sort key width: ceil(log2(ncells + 1))
@@ -54,6 +55,7 @@ struct sphk_ctx {
     float* pinned = nullptr;                     // host pinned scalar
     // ---- state ----
     int nF = 0, nB = 0;
+    int actBegin = 0, actCount = -1; // active (owned) range of the sweeps; -1: all
     int kmax = 96;
     bool useList = true, useTile = false;
     unsigned long long searchEpoch = 0, listEpoch = ~0ull;
@@ -71,7 +73,8 @@ struct DevScene {
     const int* __restrict__ cnt;
     const float* __restrict__ massRange;
     int nF, bOff, nbrStride, kmax;
-    int3 cs;
+    int iBegin, iEnd;                // sweeps compute particles [iBegin, iEnd)
+    int3 cs, org;
     float cellLength;
     KConst k;
 };

@@ -21,13 +21,13 @@
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_hash_snapshot(const float* __restrict__ pos, const float* __restrict__ vel, int n, float cellLength,
-                int3 cs, int* __restrict__ p2c, int* __restrict__ keys, int* __restrict__ idx,
+                int3 cs, int3 org, int* __restrict__ p2c, int* __restrict__ keys, int* __restrict__ idx,
                 float4* __restrict__ snapPos, float4* __restrict__ snapVel) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= n) return;
     const float3 p = load3(pos, i);
-    const int key = cell_index(cell_coord(p.x, cellLength), cell_coord(p.y, cellLength),
-                               cell_coord(p.z, cellLength), cs);
+    const int key = cell_index(cell_coord(p.x, cellLength) - org.x, cell_coord(p.y, cellLength) - org.y,
+                               cell_coord(p.z, cellLength) - org.z, cs);
     p2c[i] = key;
     keys[i] = key;
     idx[i] = i;
@@ -64,7 +64,10 @@ k_gather(const int* __restrict__ idxSorted, const float4* __restrict__ snapPos,
             lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
             hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         }
-        if ((threadIdx.x & 31) == 0) { atomicMin(massRange, __float_as_uint(lo)); atomicMax(massRange + 1, __float_as_uint(hi)); }
+        if ((threadIdx.x & 31) == 0) {      // almost never taken after the first warps: no atomic storm
+            if (__float_as_uint(lo) < massRange[0]) atomicMin(massRange, __float_as_uint(lo));
+            if (__float_as_uint(hi) > massRange[1]) atomicMax(massRange + 1, __float_as_uint(hi));
+        }
     }
 }
 
@@ -109,7 +112,10 @@ k_repack(const float* __restrict__ pos, const float* __restrict__ vel, const flo
             lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
             hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         }
-        if ((threadIdx.x & 31) == 0) { atomicMin(massRange, __float_as_uint(lo)); atomicMax(massRange + 1, __float_as_uint(hi)); }
+        if ((threadIdx.x & 31) == 0) {      // almost never taken after the first warps: no atomic storm
+            if (__float_as_uint(lo) < massRange[0]) atomicMin(massRange, __float_as_uint(lo));
+            if (__float_as_uint(hi) > massRange[1]) atomicMax(massRange + 1, __float_as_uint(hi));
+        }
     }
 }
 
@@ -172,6 +178,7 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
     c->stream = static_cast<cudaStream_t>(stream);
     c->capF = max_fluid; c->capB = max_boundary;
     c->cs = make_int3(grid->cell_size[0], grid->cell_size[1], grid->cell_size[2]);
+    c->org = make_int3(grid->origin[0], grid->origin[1], grid->origin[2]);
     c->ncells = c->cs.x * c->cs.y * c->cs.z;
     c->cellLength = grid->cell_length;
     c->endBit = 1;
@@ -267,7 +274,7 @@ extern "C" int sphk_neighbor_search(sphk_ctx* c, int which, const sphk_particles
     if (n > (fluid ? c->capF : c->capB)) return SPHK_ERR_CAPACITY;
     const int off = fluid ? 0 : c->capF;
     cudaStream_t st = c->stream;
-    k_hash_snapshot<<<sphk_blocks(n), SPHK_BLOCK, 0, st>>>(p->pos, p->vel, n, c->cellLength, c->cs, p->particle2cell,
+    k_hash_snapshot<<<sphk_blocks(n), SPHK_BLOCK, 0, st>>>(p->pos, p->vel, n, c->cellLength, c->cs, c->org, p->particle2cell,
                                                           c->keys, c->idx, c->snapA, c->snapB);
     size_t tb = c->cubTempBytes;
     SPHK_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cubTemp, tb, c->keys, c->keysSorted, c->idx, c->idxSorted, n, 0,
@@ -277,7 +284,8 @@ extern "C" int sphk_neighbor_search(sphk_ctx* c, int which, const sphk_particles
                                                    c->rec + off, fluid ? 1 : 0, reinterpret_cast<unsigned int*>(c->massRange));
     k_cell_start<<<sphk_blocks(c->ncells + 1), SPHK_BLOCK, 0, st>>>(c->keysSorted, n, c->ncells, cell_start);
     c->launches += 3 + 4;   // 3 own kernels + CUB onesweep (histogram, scan, <=3 passes): counted as 4
-    if (fluid) { c->nF = n; c->fluidSearched = true; c->permValid = true; c->searchEpoch++; c->posDirty = false; c->sTag = nullptr; }
+    if (fluid) { c->nF = n; c->fluidSearched = true; c->permValid = true; c->searchEpoch++; c->posDirty = false; c->sTag = nullptr;
+                 c->actBegin = 0; c->actCount = -1; }
     else { c->nB = n; c->boundarySearched = true; c->listEpoch = ~0ull; c->permValid = false; }
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;

@@ -266,7 +266,8 @@ __device__ __forceinline__ float uniform_mass(const DevScene& s) {
 
 template <class Op>
 __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float4 pi, float m0) {
-    const int cx = cell_coord(pi.x, s.cellLength), cy = cell_coord(pi.y, s.cellLength), cz = cell_coord(pi.z, s.cellLength);
+    const int cx = cell_coord(pi.x, s.cellLength) - s.org.x, cy = cell_coord(pi.y, s.cellLength) - s.org.y,
+              cz = cell_coord(pi.z, s.cellLength) - s.org.z;
     const float3 xi = xyz(pi);
 #pragma unroll 1
     for (int m = 0; m < 27; ++m) {
@@ -298,8 +299,8 @@ __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, type
 
 template <class Op>
 __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_cells(const DevScene s, const Op op) {
-    const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= s.nF) return;
+    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= s.iEnd) return;
     float4 lo, hi;
     rec_full(s.rec + i, lo, hi);
     typename Op::Acc acc;
@@ -319,8 +320,8 @@ __device__ __forceinline__ void list_pair(const DevScene& s, const Op& op, typen
 
 template <class Op>
 __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, const Op op) {
-    const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= s.nF) return;
+    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= s.iEnd) return;
     float4 lo, hi;
     rec_full(s.rec + i, lo, hi);
     const float3 xi = xyz(lo);
@@ -352,12 +353,13 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, con
 
 // computeBoundaryMass_CUDA, SPHSystem.cu:79-105: boundary particles against the boundary set only
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_boundary_mass(Rec* __restrict__ recB, float* __restrict__ mass, int n, const int* __restrict__ csB, int3 cs,
+k_boundary_mass(Rec* __restrict__ recB, float* __restrict__ mass, int n, const int* __restrict__ csB, int3 cs, int3 org,
                 float cellLength, float rhoB, KConst k) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= n) return;
     const float4 pi = rec_lo(recB + i);
-    const int cx = cell_coord(pi.x, cellLength), cy = cell_coord(pi.y, cellLength), cz = cell_coord(pi.z, cellLength);
+    const int cx = cell_coord(pi.x, cellLength) - org.x, cy = cell_coord(pi.y, cellLength) - org.y,
+              cz = cell_coord(pi.z, cellLength) - org.z;
     float sum = 0.f;
     for (int m = 0; m < 27; ++m) {
         const int c = cell_index(cx + m / 9 - 1, cy + (m % 9) / 3 - 1, cz + m % 3 - 1, cs);
@@ -447,9 +449,9 @@ k_vel_from_pos(Rec* __restrict__ rec, const float* __restrict__ posLast, float* 
     rec_set_vel(rec + i, v); store3(vel, i, v);
 }
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_commit_vel(const float4* __restrict__ src, Rec* __restrict__ rec, float* __restrict__ vel, int n) {
-    const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= n) return;
+k_commit_vel(const float4* __restrict__ src, Rec* __restrict__ rec, float* __restrict__ vel, int begin, int end) {
+    const int i = begin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= end) return;
     const float3 v = xyz(src[i]);
     rec_set_vel(rec + i, v);
     if (vel) store3(vel, i, v);
@@ -497,7 +499,9 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
     d.rec = c->rec; d.csF = s->cell_start_fluid; d.csB = s->cell_start_boundary;
     d.nbr = c->nbr; d.cnt = c->cnt; d.massRange = c->massRange;
     d.nF = c->nF; d.bOff = c->capF; d.nbrStride = c->capF; d.kmax = c->kmax;
-    d.cs = c->cs; d.cellLength = c->cellLength;
+    d.cs = c->cs; d.org = c->org; d.cellLength = c->cellLength;
+    d.iBegin = c->actCount < 0 ? 0 : c->actBegin;
+    d.iEnd = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
     d.k = kernel_constants(s->radius);
     return d;
 }
@@ -510,6 +514,7 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
     }
     DevScene b = d;
     b.nbr = c->nbr;
+    b.iBegin = 0; b.iEnd = c->nF;       // lists are built for every local particle (ghosts included)
     OpBuildList op{c->nbr, c->cnt};
     k_sweep_cells<OpBuildList><<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(b, op);
     c->launches++;
@@ -519,14 +524,15 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
 
 template <class Op> static int run_sweep(sphk_ctx* c, const sphk_scene* s, const Op& op) {
     DevScene d = dev_scene(c, s);
+    if (d.iEnd <= d.iBegin) return SPHK_OK;
     const bool list = c->useList && !c->posDirty;
     if (list) {
         const int rc = ensure_list(c, d);
         if (rc != SPHK_OK) return rc;
         d.nbr = c->nbr;
-        k_sweep_list<Op><<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(d, op);
+        k_sweep_list<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     } else {
-        k_sweep_cells<Op><<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(d, op);
+        k_sweep_cells<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     }
     c->launches++;
     SPHK_CUDA_TRY(cudaGetLastError());
@@ -547,7 +553,7 @@ extern "C" int sphk_boundary_mass(sphk_ctx* c, const sphk_particles* b, const in
     if (!c || !b || !csB || !b->mass) return SPHK_ERR_INVALID;
     if (!c->boundarySearched || b->n != c->nB) return SPHK_ERR_STATE;
     Rec* recB = c->rec + c->capF;
-    k_boundary_mass<<<sphk_blocks(c->nB), SPHK_BLOCK, 0, c->stream>>>(recB, b->mass, c->nB, csB, c->cs, c->cellLength, rhoB,
+    k_boundary_mass<<<sphk_blocks(c->nB), SPHK_BLOCK, 0, c->stream>>>(recB, b->mass, c->nB, csB, c->cs, c->org, c->cellLength, rhoB,
                                                                      kernel_constants(R));
     k_set_mass<<<sphk_blocks(c->nB), SPHK_BLOCK, 0, c->stream>>>(recB, b->mass, c->nB);
     c->launches += 2;
@@ -575,7 +581,8 @@ extern "C" int sphk_viscosity(sphk_ctx* c, const sphk_scene* s, float* delta_v, 
     OpViscosity op{tmp, s->fluid.vel, delta_v, rho0, visc, dt};
     const int rc = run_sweep(c, s, op);
     if (rc != SPHK_OK) return rc;
-    k_commit_vel<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, nullptr, c->nF);
+    const int b = c->actCount < 0 ? 0 : c->actBegin, e = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
+    if (e > b) k_commit_vel<<<sphk_blocks(e - b), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, nullptr, b, e);
     c->launches++;
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;
@@ -720,7 +727,36 @@ extern "C" int sphk_pbd_xsph(sphk_ctx* c, const sphk_scene* s, float xc, float r
     OpXsph op{tmp, xc, rho0};
     const int rc = run_sweep(c, s, op);
     if (rc != SPHK_OK) return rc;
-    k_commit_vel<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, s->fluid.vel, c->nF);
+    const int b = c->actCount < 0 ? 0 : c->actBegin, e = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
+    if (e > b) k_commit_vel<<<sphk_blocks(e - b), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, s->fluid.vel, b, e);
+    c->launches++;
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_push_range(Rec* __restrict__ rec, const float* __restrict__ vel, const float* __restrict__ scalar, int begin, int count) {
+    const int t = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (t >= count) return;
+    const int i = begin + t;
+    if (vel) rec_set_vel(rec + i, load3(vel, i));
+    if (scalar) rec[i].s = scalar[i];
+}
+
+extern "C" int sphk_set_active_range(sphk_ctx* c, int begin, int count) {
+    if (!c) return SPHK_ERR_INVALID;
+    if (count >= 0 && (begin < 0 || begin + count > c->nF)) return SPHK_ERR_INVALID;
+    c->actBegin = begin; c->actCount = count;
+    return SPHK_OK;
+}
+
+extern "C" int sphk_push_range(sphk_ctx* c, const sphk_scene* s, int what, const float* array, int begin, int count) {
+    SPHK_CHECK_SCENE(c, s);
+    if (begin < 0 || count < 0 || begin + count > c->nF || what < 1 || what > 3) return SPHK_ERR_INVALID;
+    if ((what & 2) && !array) return SPHK_ERR_INVALID;
+    if (count == 0) return SPHK_OK;
+    k_push_range<<<sphk_blocks(count), SPHK_BLOCK, 0, c->stream>>>(c->rec, (what & 1) ? s->fluid.vel : nullptr,
+                                                                  (what & 2) ? array : nullptr, begin, count);
     c->launches++;
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;

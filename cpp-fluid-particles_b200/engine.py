@@ -45,33 +45,35 @@ class ParticleSet:
         return p
 
 
-class SphkSystem:
-    """SPHSystem + solver over the C-ABI with torch tensors.  construct(step0=True) reproduces the
-    reference constructor including its implicit first step (Q3)."""
+class SphkOps:
+    """The C-ABI calls and the three solver sequences over torch tensors.  Subclasses provide the tensors
+    (fluid, boundary, cs_fluid, cs_boundary, solver buffers), ctx and params.  The sync_* hooks are no-ops on
+    one GPU; the slab driver overrides them with halo exchanges."""
 
-    def __init__(self, scene, device="cuda:0", use_list: bool | None = None, list_capacity: int | None = None,
-                 step0: bool = True):
-        self.L = capi.sphk()
-        self.p = scene.params
-        self.device = torch.device(device)
-        torch.cuda.set_device(self.device)
-        self.stream = torch.cuda.current_stream(self.device)
-        self.fluid = ParticleSet(scene.fluid, self.device)
-        self.boundary = ParticleSet(scene.boundary, self.device)
-        nc = self.p.ncells
-        self.cs_fluid = torch.zeros(nc + 1, dtype=torch.int32, device=self.device)
-        self.cs_boundary = torch.zeros(nc + 1, dtype=torch.int32, device=self.device)
-        g = SphkGrid()
-        g.cell_size[:] = [int(c) for c in self.p.cell_size]
-        g.cell_length = self.p.cell_length
-        self.ctx = C.c_void_p()
-        check(self.L.sphk_create(C.byref(self.ctx), C.c_int(self.fluid.n), C.c_int(self.boundary.n), C.byref(g),
-                                 C.c_void_p(self.stream.cuda_stream)), "sphk_create")
-        if list_capacity is not None:
-            check(self.L.sphk_set_option(self.ctx, capi.OPT_LIST_CAPACITY, int(list_capacity)))
-        self.solver = self.p.solver
-        self.use_list = (self.solver != "pbd") if use_list is None else bool(use_list)
-        n = self.fluid.n
+    # ---- multi-GPU hooks ---------------------------------------------------------------------------------
+    def sync_vel(self):
+        pass
+
+    def sync_scalar(self, t):
+        pass
+
+    def sync_array(self, t):
+        pass
+
+    def sync_positions(self):
+        pass
+
+    def reduce_sum(self, x: float) -> float:
+        return x
+
+    def owned(self, t):
+        """The slice of a per-particle tensor this rank owns (all of it on one GPU)."""
+        return t
+
+    def n_total(self) -> int:
+        return self.fluid.n
+
+    def _alloc_solver_buffers(self, n):
         dev = self.device
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
         self.buffer3 = f(n, 3)          # BasicSPHSolver::bufferFloat3
@@ -86,16 +88,6 @@ class SphkSystem:
             self.max_iter = self.p.max_iter if self.p.max_iter > 0 else 20
             self.xsph_c, self.relaxation = 0.05, 0.75
         self.it_div = self.it_den = 0
-        self._scene = None
-        self._G = (C.c_float * 3)(*[float(x) for x in self.p.gravity])
-        self._space = (C.c_float * 3)(*[float(x) for x in self.p.space])
-        # SPHSystem.cu:68-76
-        self.search_boundary()
-        self.boundary_mass()
-        check(self.L.sphk_fill(self.ctx, _ptr(self.fluid.mass), C.c_int(n), C.c_float(self.p.m0)), "sphk_fill")
-        self.search_fluid()
-        if step0:
-            self.step()
 
     # ---- C-ABI plumbing ---------------------------------------------------------------------------
     def scene_abi(self) -> SphkScene:
@@ -236,40 +228,45 @@ class SphkSystem:
     def step_wcsph(self):            # BasicSPHSolver.cu:237-260
         self.set_use_list(self.use_list)
         self.gravity()
-        self.viscosity()
-        self._handle_surface()
+        self.viscosity(); self.sync_vel()
+        if self._surface_enabled():  # handleSurface, :262-275
+            self.color_grad(); self.sync_array(self.buffer3)
+            self.surface(); self.sync_vel()
         self.density()
         self.pressure()
+        self.sync_array(self.fluid.density); self.sync_array(self.fluid.pressure)
         self.pressure_force()
         self.advect()
 
     def step_dfsph(self):            # DFSPHSolver.cu:33-72
         self.set_use_list(self.use_list)
-        n, rho0 = self.fluid.n, self.p.rho0
+        n, rho0 = self.n_total(), self.p.rho0
         self.dfsph_density_alpha()
         total, it = 3.4e38, 0        # correctDivergenceError :331-363
-        self.dfsph_div_error()
+        self.dfsph_div_error(); self.sync_scalar(self.kappa)
         while (it < 1 or total > self.div_thr * n * rho0) and it < self.max_iter:
-            self.dfsph_div_correct()
-            self.dfsph_div_error()
+            self.dfsph_div_correct(); self.sync_vel()
+            self.dfsph_div_error(); self.sync_scalar(self.kappa)
             it += 1
-            if self.div_thr >= 0:
-                total = self.reduce_abs_sum(self.error)
+            if self.div_thr >= 0:    # negative threshold: the test cannot depend on the sum (Q11) -> no host sync
+                total = self.reduce_sum(self.reduce_abs_sum(self.owned(self.error)))
         self.it_div = it
         self.gravity()
-        self.viscosity()
-        self._handle_surface()
+        self.viscosity(); self.sync_vel()
+        if self._surface_enabled():
+            self.color_grad(); self.sync_array(self.buffer3)
+            self.surface(); self.sync_vel()
         total, it = 3.4e38, 0        # project :160-210
         self.permute(self.warm, 1)
-        self.dfsph_den_correct(self.warm)
-        self.dfsph_den_error(False)
+        self.dfsph_den_correct(self.warm); self.sync_vel()
+        self.dfsph_den_error(False); self.sync_scalar(self.kappa)
         self.copy(self.warm, self.kappa)
         while (it < 2 or total > self.den_thr * n * rho0) and it < self.max_iter:
-            self.dfsph_den_correct()
-            self.dfsph_den_error(True)
+            self.dfsph_den_correct(); self.sync_vel()
+            self.dfsph_den_error(True); self.sync_scalar(self.kappa)
             it += 1
             if it >= 2 and self.den_thr >= 0:
-                total = self.reduce_abs_sum(self.error)
+                total = self.reduce_sum(self.reduce_abs_sum(self.owned(self.error)))
         self.it_den = it
         self.advect()
 
@@ -281,11 +278,13 @@ class SphkSystem:
         self.set_use_list(False)
         self.permute(self.pos_last, 3)
         for _ in range(self.max_iter):
-            self.pbd_density_lambda()
-            self.pbd_delta_pos_apply()
+            self.pbd_density_lambda(); self.sync_scalar(self.lam)
+            self.pbd_delta_pos_apply(); self.sync_positions()
         self.pbd_velocity_from_positions()
-        self.pbd_xsph()
-        self._handle_surface()
+        self.pbd_xsph(); self.sync_vel()
+        if self._surface_enabled():
+            self.color_grad(); self.sync_array(self.buffer3)
+            self.surface(); self.sync_vel()
         self.gravity()
         self.copy(self.pos_last, self.fluid.pos)
         self.advect()
@@ -319,3 +318,43 @@ class SphkSystem:
             self.close()
         except Exception:
             pass
+
+
+class SphkSystem(SphkOps):
+    """SPHSystem + solver over the C-ABI with torch tensors.  construct(step0=True) reproduces the
+    reference constructor including its implicit first step (Q3)."""
+
+    def __init__(self, scene, device="cuda:0", use_list: bool | None = None, list_capacity: int | None = None,
+                 step0: bool = True):
+        self.L = capi.sphk()
+        self.p = scene.params
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        self.fluid = ParticleSet(scene.fluid, self.device)
+        self.boundary = ParticleSet(scene.boundary, self.device)
+        nc = self.p.ncells
+        self.cs_fluid = torch.zeros(nc + 1, dtype=torch.int32, device=self.device)
+        self.cs_boundary = torch.zeros(nc + 1, dtype=torch.int32, device=self.device)
+        g = SphkGrid()
+        g.cell_size[:] = [int(c) for c in self.p.cell_size]
+        g.cell_length = self.p.cell_length
+        self.ctx = C.c_void_p()
+        check(self.L.sphk_create(C.byref(self.ctx), C.c_int(self.fluid.n), C.c_int(self.boundary.n), C.byref(g),
+                                 C.c_void_p(self.stream.cuda_stream)), "sphk_create")
+        if list_capacity is not None:
+            check(self.L.sphk_set_option(self.ctx, capi.OPT_LIST_CAPACITY, int(list_capacity)))
+        self.solver = self.p.solver
+        self.use_list = (self.solver != "pbd") if use_list is None else bool(use_list)
+        n = self.fluid.n
+        self._alloc_solver_buffers(n)
+        self._scene = None
+        self._G = (C.c_float * 3)(*[float(x) for x in self.p.gravity])
+        self._space = (C.c_float * 3)(*[float(x) for x in self.p.space])
+        # SPHSystem.cu:68-76
+        self.search_boundary()
+        self.boundary_mass()
+        check(self.L.sphk_fill(self.ctx, _ptr(self.fluid.mass), C.c_int(n), C.c_float(self.p.m0)), "sphk_fill")
+        self.search_fluid()
+        if step0:
+            self.step()

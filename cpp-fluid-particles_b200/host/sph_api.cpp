@@ -19,6 +19,7 @@ Engine::Engine(int maxFluid, int maxBoundary, int3 cellSize, float cellLength) {
     sphk_grid g;
     g.cell_size[0] = cellSize.x; g.cell_size[1] = cellSize.y; g.cell_size[2] = cellSize.z;
     g.cell_length = cellLength;
+    g.origin[0] = g.origin[1] = g.origin[2] = 0;
     const int rc = sphk_create(&ctx_, maxFluid, maxBoundary, &g, stream_);
     if (rc != 0) {
         // no CPU fallback: a missing device / failed allocation is reported and leaves the system inert

@@ -52,17 +52,19 @@ CELL_LENGTH = F(1.01) * RADIUS                      # main.cpp:57
 M0 = F(76.596750762082e-6)                          # main.cpp:61
 
 
-def default_params(box: float, solver: str = "wcsph", dt: float | None = None, max_iter: int = 0,
+def default_params(box, solver: str = "wcsph", dt: float | None = None, max_iter: int = 0,
                    den_thr: float = 1e-3, div_thr: float = 1e-3) -> SceneParams:
-    L = F(box)
-    ncell = int(math.ceil(float(L / CELL_LENGTH)))   # main.cpp:67 (float divide, then ceil)
+    """box: edge length (the reference's cubic spaceSize, main.cpp:54) or a per-axis (Lx, Ly, Lz) tuple
+    (weak-scaling scenes stretch the box; the SPHSystem API takes float3 spaceSize / int3 cellSize anyway)."""
+    Ls = tuple(F(b) for b in (box if isinstance(box, (tuple, list)) else (box,) * 3))
+    ncells = tuple(int(math.ceil(float(L / CELL_LENGTH))) for L in Ls)   # main.cpp:67 (float divide, then ceil)
     if dt is None:
         dt = 0.001 if solver in ("wcsph", "sph") else 0.004   # README.md:7-9 / BASELINE.md
-    return SceneParams(space=(float(L),) * 3, cell_length=float(CELL_LENGTH), radius=float(RADIUS),
+    return SceneParams(space=tuple(float(L) for L in Ls), cell_length=float(CELL_LENGTH), radius=float(RADIUS),
                        dt=float(F(dt)), m0=float(M0), rho0=1.0, rho_boundary=float(F(1.4) * F(1.0)),
                        stiff=10.0, visc=float(F(5e-4)), surface_tension=float(F(1e-4)),
                        air_pressure=float(F(1e-4)), gravity=(0.0, float(F(-9.8)), 0.0),
-                       cell_size=(ncell,) * 3, solver=solver, max_iter=max_iter,
+                       cell_size=ncells, solver=solver, max_iter=max_iter,
                        density_error_threshold=den_thr, divergence_error_threshold=div_thr)
 
 
@@ -124,7 +126,12 @@ _CONFIGS = {
     "config0": (1.0, (24, 36, 24), (0.27, 0.10, 0.27)),
     "200k": (2.0, (60, 60, 60), (0.365, 0.105, 0.365)),
     "2m": (4.0, (128, 128, 128), (0.725, 0.105, 0.725)),
+    # weak-scaling family: 2M fluid particles per GPU (x, then z, then y doubled); 16m is BASELINE configs[4]
+    "4m": ((8.0, 4.0, 4.0), (256, 128, 128), (0.725, 0.105, 0.725)),
+    "8m": ((8.0, 4.0, 8.0), (256, 128, 256), (0.725, 0.105, 0.725)),
     "16m": (8.0, (256, 256, 256), (1.445, 0.105, 1.445)),
+    # small multi-rank test scene (x-long block so that 2-4 slabs all own fluid)
+    "slabtest": ((2.0, 1.0, 1.0), (64, 24, 24), (0.285, 0.105, 0.285)),
 }
 
 

@@ -47,6 +47,8 @@ typedef struct sphk_ctx sphk_ctx;
 typedef struct sphk_grid {
     int   cell_size[3];
     float cell_length;
+    int   origin[3];   /* cell coordinates of this context's cell (0,0,0) in the global grid: all zero for a
+                          single-GPU system; a slab rank covers global x-planes [origin[0], origin[0]+cell_size[0]) */
 } sphk_grid;
 
 /* One SPHParticles object (SPHParticles.h:56-59 + Particles.h:47-48): device pointers. */
@@ -164,6 +166,16 @@ int sphk_pbd_delta_pos_apply(sphk_ctx* ctx, const sphk_scene* s, const float* la
 int sphk_pbd_velocity_from_positions(sphk_ctx* ctx, const sphk_scene* s, const float* pos_last, float dt);
 /* XSPHViscosity_CUDA, PBDSolver.cu:89-125; Jacobi (the reference updates in place and races, Q5) */
 int sphk_pbd_xsph(sphk_ctx* ctx, const sphk_scene* s, float c, float rho0);
+
+/* ---- multi-GPU slab support (no reference counterpart: the reference is single-GPU) ----------------
+ * A slab rank keeps [ghost-left | owned | ghost-right] particles in one sorted set (cpp-fluid-particles_b200/
+ * slabs.py).  Sweeps compute only the active (owned) range; ghost values arrive by halo exchange of the API
+ * arrays (contiguous slices, sent with NCCL by the host) followed by sphk_push_range. */
+/* restrict every subsequent sweep to particles [begin, begin+count) of the fluid set (count<0: all) */
+int sphk_set_active_range(sphk_ctx* ctx, int begin, int count);
+/* copy API data of particles [begin, begin+count) into the packed records: what = 1: vel (scene->fluid.vel),
+ * 2: neighbour scalar from `array` (float[n]); 3: vel and scalar */
+int sphk_push_range(sphk_ctx* ctx, const sphk_scene* s, int what, const float* array, int begin, int count);
 
 /* ---- introspection for parity tests --------------------------------------------------------- */
 /* copies the stable-sort permutation of the last fluid search (perm[s] = pre-sort index) to device

@@ -1,0 +1,41 @@
+"""Multi-rank slab driver against the single-GPU result (<= 1e-5 on pos / density, north_star).
+On a 1-GPU box the ranks share cuda:0 (gloo, host-staged halo); with >= 2 GPUs the NCCL path runs too."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from util import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(nproc, extra, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + nproc + len(extra)),
+           os.path.join(ROOT, "tools", "slab_check.py")] + extra
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, cwd=ROOT)
+    line = [l for l in r.stdout.splitlines() if l.startswith("SLAB_CHECK ")]
+    assert r.returncode == 0 and line, r.stdout[-3000:]
+    return json.loads(line[-1][len("SLAB_CHECK "):])
+
+
+@pytest.mark.parametrize("solver", ["dfsph", "wcsph"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_slabs_match_single_gpu_shared_device(built, solver, world):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device")
+    out = _run(world, ["--backend", "gloo", "--same-gpu", "--solver", solver, "--steps", "3", "--jitter", "0.001"])
+    assert out["ok"], out
+    assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
+
+
+def test_slabs_match_single_gpu_nccl(built):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    out = _run(2, ["--backend", "nccl", "--solver", "dfsph", "--steps", "3"])
+    assert out["ok"], out
