@@ -234,8 +234,8 @@ class SlabSystem(SphkOps):
         self.rows = torch.zeros((cap, 6 + self.hist), dtype=torch.float32, device=self.device)
         self.n_own, self.n_gl, self.n_gr = mine.shape[0], 0, 0
         # boundary: already in global sorted order -> identity permutation; masses given (not recomputed)
+        # (the search's gather packs mass[s] of the sorted slot s into the records: the masses set above)
         self.search_boundary()
-        self.refresh_boundary_mass()
         self.comm_s = 0.0
         self.step()                                     # the constructor's implicit step 0 (Q3)
 
@@ -263,12 +263,6 @@ class SlabSystem(SphkOps):
         self._bplane = np.searchsorted(plane_start, np.arange(nb), side="right") - 1
         self.L.sphk_destroy(ctx)
         return pos, mass
-
-    def refresh_boundary_mass(self):
-        """The local boundary records take the globally computed masses (no local recomputation)."""
-        s = self.scene_abi()
-        # k_repack of the boundary part: sphk_refresh re-packs both sets from the API arrays
-        check(self.L.sphk_refresh(self.ctx, C.byref(s)), "sphk_refresh")
 
     # ---- step ---------------------------------------------------------------------------------------------
     def _pack_rows(self, n):
