@@ -330,30 +330,20 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, con
     const int n = s.cnt[i];
     const float m0 = uniform_mass(s);
     if (n <= s.kmax) {
-        // two-deep software pipeline: indices of batch b+2 and records of batch b+1 are in flight while the
-        // math of batch b runs (8 independent gathers outstanding per thread)
         const int nb4 = (n + 3) >> 2;
         const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + i;
-        const int4 self4 = make_int4(i, i, i, i);
-        int4 jc = self4, jn = self4;
-        if (nb4 > 0) jc = __ldcs(row);
-        if (nb4 > 1) jn = __ldcs(row + s.nbrStride);
-        row += 2 * static_cast<size_t>(s.nbrStride);
-        float4 l0, h0, l1, h1, l2, h2, l3, h3;
-        fetch<Op>(s, jc.x, l0, h0); fetch<Op>(s, jc.y, l1, h1); fetch<Op>(s, jc.z, l2, h2); fetch<Op>(s, jc.w, l3, h3);
+        int4 jn = make_int4(i, i, i, i);
+        if (nb4 > 0) jn = __ldcs(row);
         for (int b = 0; b < nb4; ++b) {
-            const int4 j4 = jc;
-            const float4 a0 = l0, b0 = h0, a1 = l1, b1 = h1, a2 = l2, b2 = h2, a3 = l3, b3 = h3;
-            jc = jn;
-            if (b + 1 < nb4) {
-                fetch<Op>(s, jc.x, l0, h0); fetch<Op>(s, jc.y, l1, h1); fetch<Op>(s, jc.z, l2, h2); fetch<Op>(s, jc.w, l3, h3);
-                if (b + 2 < nb4) jn = __ldcs(row);
-                row += s.nbrStride;
-            }
-            list_pair(s, op, acc, i, xi, j4.x, a0, b0, m0);
-            list_pair(s, op, acc, i, xi, j4.y, a1, b1, m0);
-            list_pair(s, op, acc, i, xi, j4.z, a2, b2, m0);
-            list_pair(s, op, acc, i, xi, j4.w, a3, b3, m0);
+            const int4 j4 = jn;
+            row += s.nbrStride;
+            if (b + 1 < nb4) jn = __ldcs(row);
+            float4 l0, h0, l1, h1, l2, h2, l3, h3;
+            fetch<Op>(s, j4.x, l0, h0); fetch<Op>(s, j4.y, l1, h1); fetch<Op>(s, j4.z, l2, h2); fetch<Op>(s, j4.w, l3, h3);
+            list_pair(s, op, acc, i, xi, j4.x, l0, h0, m0);
+            list_pair(s, op, acc, i, xi, j4.y, l1, h1, m0);
+            list_pair(s, op, acc, i, xi, j4.z, l2, h2, m0);
+            list_pair(s, op, acc, i, xi, j4.w, l3, h3, m0);
         }
     } else {
         walk_cells(s, op, acc, i, lo, m0);  // more neighbours than the list keeps: exact fallback
