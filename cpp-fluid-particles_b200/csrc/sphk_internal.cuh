@@ -57,7 +57,7 @@ struct sphk_ctx {
     int nF = 0, nB = 0;
     int actBegin = 0, actCount = -1; // active (owned) range of the sweeps; -1: all
     int kmax = 96;
-    bool useList = true, useTile = false, brickOrder = true;
+    bool useList = true, useTile = false;
     unsigned long long searchEpoch = 0, listEpoch = ~0ull;
     bool posDirty = false;
     bool fluidSearched = false, boundarySearched = false, permValid = false;

@@ -230,7 +230,6 @@ extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
         }
         return SPHK_OK;
     case SPHK_OPT_TILE_SWEEP: c->useTile = value != 0; return SPHK_OK;
-    case SPHK_OPT_BRICK_ORDER: c->brickOrder = value != 0; return SPHK_OK;
     default: return SPHK_ERR_INVALID;
     }
 }

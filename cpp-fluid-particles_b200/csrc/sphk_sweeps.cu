@@ -319,7 +319,9 @@ __device__ __forceinline__ void list_pair(const DevScene& s, const Op& op, typen
 }
 
 template <class Op>
-__device__ __forceinline__ void sweep_one_list(const DevScene& s, const Op& op, int i) {
+__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, const Op op) {
+    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= s.iEnd) return;
     float4 lo, hi;
     rec_full(s.rec + i, lo, hi);
     const float3 xi = xyz(lo);
@@ -347,56 +349,6 @@ __device__ __forceinline__ void sweep_one_list(const DevScene& s, const Op& op, 
         walk_cells(s, op, acc, i, lo, m0);  // more neighbours than the list keeps: exact fallback
     }
     op.end(acc, i, lo, hi, s);
-}
-
-template <class Op>
-__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, const Op op) {
-    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= s.iEnd) return;
-    sweep_one_list(s, op, i);
-}
-
-// Brick-ordered traversal: a thread block owns a compact BX x BY x BZ brick of cells (the particle ORDER in
-// memory stays the reference's x-major order -- only the thread -> particle assignment changes).  A 1 x 1 x 16
-// column of cells (128 consecutive particles) touches ~10x its own size in neighbour records; a 4 x 4 x 8 brick
-// touches ~2.8x, so the gathers of co-resident warps hit in L1 instead of going to L2 (ncu: L1 hit rate,
-// profiles/).  The brick's particles are BX*BY contiguous runs (one per (x,y) row), found from cellStart.
-#define SPHK_BRICK_X 4
-#define SPHK_BRICK_Y 4
-#define SPHK_BRICK_Z 8
-#define SPHK_BRICK_THREADS 256
-template <class Op>
-__global__ void __launch_bounds__(SPHK_BRICK_THREADS) k_sweep_list_brick(const DevScene s, const Op op, int nby, int nbz) {
-    constexpr int ROWS = SPHK_BRICK_X * SPHK_BRICK_Y;
-    __shared__ int rowStart[ROWS], rowPrefix[ROWS + 1];
-    const int bz = blockIdx.x % nbz, by = (blockIdx.x / nbz) % nby, bx = blockIdx.x / (nbz * nby);
-    if (threadIdx.x < ROWS) {
-        const int x = bx * SPHK_BRICK_X + threadIdx.x / SPHK_BRICK_Y, y = by * SPHK_BRICK_Y + threadIdx.x % SPHK_BRICK_Y;
-        int start = 0, count = 0;
-        if (x < s.cs.x && y < s.cs.y) {
-            const int z0 = bz * SPHK_BRICK_Z, z1 = min(z0 + SPHK_BRICK_Z, s.cs.z);
-            const int c0 = (x * s.cs.y + y) * s.cs.z + z0;
-            start = s.csF[c0];
-            count = s.csF[c0 + (z1 - z0)] - start;
-        }
-        rowStart[threadIdx.x] = start;
-        rowPrefix[threadIdx.x + 1] = count;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        rowPrefix[0] = 0;
-        for (int r = 0; r < ROWS; ++r) { run += rowPrefix[r + 1]; rowPrefix[r + 1] = run; }
-    }
-    __syncthreads();
-    const int total = rowPrefix[ROWS];
-    for (int p = threadIdx.x; p < total; p += SPHK_BRICK_THREADS) {
-        int r = 0;
-#pragma unroll
-        for (int step = ROWS / 2; step > 0; step >>= 1) if (rowPrefix[r + step] <= p) r += step;
-        const int i = rowStart[r] + (p - rowPrefix[r]);
-        if (i >= s.iBegin && i < s.iEnd) sweep_one_list(s, op, i);
-    }
 }
 
 // computeBoundaryMass_CUDA, SPHSystem.cu:79-105: boundary particles against the boundary set only
@@ -578,13 +530,7 @@ template <class Op> static int run_sweep(sphk_ctx* c, const sphk_scene* s, const
         const int rc = ensure_list(c, d);
         if (rc != SPHK_OK) return rc;
         d.nbr = c->nbr;
-        if (c->brickOrder) {
-            const int nbx = (c->cs.x + SPHK_BRICK_X - 1) / SPHK_BRICK_X, nby = (c->cs.y + SPHK_BRICK_Y - 1) / SPHK_BRICK_Y,
-                      nbz = (c->cs.z + SPHK_BRICK_Z - 1) / SPHK_BRICK_Z;
-            k_sweep_list_brick<Op><<<nbx * nby * nbz, SPHK_BRICK_THREADS, 0, c->stream>>>(d, op, nby, nbz);
-        } else {
-            k_sweep_list<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
-        }
+        k_sweep_list<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     } else {
         k_sweep_cells<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     }

@@ -77,9 +77,7 @@ enum {
                                     27 cells (PBD moves positions inside a step, Q7).  default 1 */
     SPHK_OPT_LIST_CAPACITY = 2,  /* max neighbours kept per particle; particles with more fall back
                                     to the cell walk individually.  default 96 */
-    SPHK_OPT_TILE_SWEEP = 3,     /* 1: cell-walk sweeps use the TMA-staged shared-memory tile kernel */
-    SPHK_OPT_BRICK_ORDER = 4     /* 1 (default): list sweeps assign thread blocks to compact bricks of cells (L1
-                                    locality); 0: thread i <-> particle i */
+    SPHK_OPT_TILE_SWEEP = 3      /* 1: cell-walk sweeps use the TMA-staged shared-memory tile kernel */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
