@@ -31,7 +31,7 @@ SPH_APP_FUNCTIONS = [
     "sph_app_download_fluid", "sph_app_download_boundary", "sph_app_upload_fluid", "sph_app_engine",
 ]
 
-OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_TILE_SWEEP = 1, 2, 3
+OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_TILE_SWEEP, OPT_LANES_PER_PARTICLE = 1, 2, 3, 4
 
 
 class SphkGrid(C.Structure):

@@ -230,6 +230,9 @@ extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
         }
         return SPHK_OK;
     case SPHK_OPT_TILE_SWEEP: c->useTile = value != 0; return SPHK_OK;
+    case SPHK_OPT_LANES_PER_PARTICLE:
+        if (value != 1 && value != 4) return SPHK_ERR_INVALID;
+        c->lanesPerParticle = value; return SPHK_OK;
     default: return SPHK_ERR_INVALID;
     }
 }

@@ -35,7 +35,7 @@
 struct OpDensity {
     float* density;
     static constexpr bool kFluidOnly = false, kHi = false;
-    struct Acc { float rho; };
+    struct Acc { float rho; template <class F> __device__ void sums(F f) { f(rho); } };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.rho = 0.f; }
     __device__ void pair(Acc& a, int, int, bool, float3, float r2, float mj, float4 lo, float4, const DevScene& s) const {
         a.rho += mj * w_cubic(sqrtf(r2), s.k);
@@ -48,7 +48,7 @@ struct OpDensity {
 struct OpPressureForce {
     Rec* rec; float* vel; float dt;
     static constexpr bool kFluidOnly = false, kHi = false;
-    struct Acc { float3 a; float pri; };
+    struct Acc { float3 a; float pri; template <class F> __device__ void sums(F f) { f(a.x); f(a.y); f(a.z); } };
     __device__ void begin(Acc& a, int, float4 lo, float4, const DevScene&) const { a.a = f3(0, 0, 0); a.pri = lo.w; }
     __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
         // `i != j` of BasicSPHSolver.cu:120 is implied: the self pair has d = 0 and contributes 0
@@ -67,7 +67,7 @@ struct OpPressureForce {
 struct OpViscosity {
     float4* velNew; float* vel; float* deltaV; float rho0, visc, dt;
     static constexpr bool kFluidOnly = true, kHi = true;
-    struct Acc { float3 a; float3 vi; };
+    struct Acc { float3 a; float3 vi; template <class F> __device__ void sums(F f) { f(a.x); f(a.y); f(a.z); } };
     __device__ void begin(Acc& a, int, float4, float4 hi, const DevScene&) const { a.a = f3(0, 0, 0); a.vi = xyz(hi); }
     __device__ void pair(Acc& a, int, int, bool, float3, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
         a.a += mj * ((xyz(hi) - a.vi) / rho0) * lap_visc(sqrtf(r2), s.k);
@@ -84,7 +84,7 @@ struct OpViscosity {
 struct OpColorGrad {
     float* colorGrad; float rho0, rhoB;
     static constexpr bool kFluidOnly = false, kHi = false;
-    struct Acc { float3 num; float den; };
+    struct Acc { float3 num; float den; template <class F> __device__ void sums(F f) { f(num.x); f(num.y); f(num.z); f(den); } };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.num = f3(0, 0, 0); a.den = 0.f; }
     __device__ void pair(Acc& a, int, int, bool isB, float3 d, float r2, float mj, float4 lo, float4, const DevScene& s) const {
         const float r = sqrtf(r2);
@@ -99,7 +99,7 @@ struct OpColorGrad {
 struct OpSurface {
     Rec* rec; float* vel; float dt, rho0, kappa, airP;
     static constexpr bool kFluidOnly = true, kHi = false;
-    struct Acc { float3 a; float cii, ratio; };
+    struct Acc { float3 a; float cii, ratio; template <class F> __device__ void sums(F f) { f(a.x); f(a.y); f(a.z); } };
     __device__ void begin(Acc& a, int, float4 lo, float4, const DevScene&) const {
         a.a = f3(0, 0, 0);
         a.cii = lo.w;
@@ -122,7 +122,7 @@ struct OpSurface {
 struct OpDensityAlpha {
     float* density; float* alpha;
     static constexpr bool kFluidOnly = false, kHi = false;
-    struct Acc { float den, lam; float3 gs; };
+    struct Acc { float den, lam; float3 gs; template <class F> __device__ void sums(F f) { f(den); f(lam); f(gs.x); f(gs.y); f(gs.z); } };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.den = 0.f; a.lam = 0.f; a.gs = f3(0, 0, 0); }
     __device__ void pair(Acc& a, int, int, bool isB, float3 d, float r2, float mj, float4 lo, float4, const DevScene& s) const {
         const float r = sqrtf(r2);
@@ -144,7 +144,7 @@ template <bool kDensity> struct OpDfsphError {
     Rec* rec; const float* density; const float* alpha; float* error; float* stiff; float* warm;
     float dt, rho0;
     static constexpr bool kFluidOnly = false, kHi = true;
-    struct Acc { float e; float3 vi; };
+    struct Acc { float e; float3 vi; template <class F> __device__ void sums(F f) { f(e); } };
     __device__ void begin(Acc& a, int, float4, float4 hi, const DevScene&) const { a.e = 0.f; a.vi = xyz(hi); }
     __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
         a.e += mj * dot3(a.vi - xyz(hi), d * grad_w_factor(sqrtf(r2), s.k));
@@ -169,7 +169,7 @@ template <bool kDensity> struct OpDfsphError {
 template <int kMode /*0: vel += a, 1: vel += a/dt, 2: deltaPos = a/rho0*/> struct OpScalarGradient {
     Rec* rec; float* vel; float* deltaPos; float dt_or_rho0;
     static constexpr bool kFluidOnly = false, kHi = false;
-    struct Acc { float3 a; float ki; };
+    struct Acc { float3 a; float ki; template <class F> __device__ void sums(F f) { f(a.x); f(a.y); f(a.z); } };
     __device__ void begin(Acc& a, int, float4 lo, float4, const DevScene&) const { a.a = f3(0, 0, 0); a.ki = lo.w; }
     __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
         a.a += mj * (a.ki + lo.w) * (d * grad_w_factor(sqrtf(r2), s.k));
@@ -186,7 +186,7 @@ template <int kMode /*0: vel += a, 1: vel += a/dt, 2: deltaPos = a/rho0*/> struc
 struct OpPbdLambda {
     Rec* rec; float* density; float* lambda; float rho0, rho0AsBool, relaxation;
     static constexpr bool kFluidOnly = false, kHi = false;
-    struct Acc { float den, lam; float3 gs; };
+    struct Acc { float den, lam; float3 gs; template <class F> __device__ void sums(F f) { f(den); f(lam); f(gs.x); f(gs.y); f(gs.z); } };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.den = 0.f; a.lam = 0.f; a.gs = f3(0, 0, 0); }
     __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float mj, float4 lo, float4, const DevScene& s) const {
         const float r = sqrtf(r2);
@@ -208,7 +208,7 @@ struct OpPbdLambda {
 struct OpXsph {
     float4* velNew; float c, rho0;
     static constexpr bool kFluidOnly = true, kHi = true;
-    struct Acc { float3 a; float3 vi; };
+    struct Acc { float3 a; float3 vi; template <class F> __device__ void sums(F f) { f(a.x); f(a.y); f(a.z); } };
     __device__ void begin(Acc& a, int, float4, float4 hi, const DevScene&) const { a.a = f3(0, 0, 0); a.vi = xyz(hi); }
     __device__ void pair(Acc& a, int, int, bool, float3, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
         a.a += mj * (xyz(hi) - a.vi) * w_cubic(sqrtf(r2), s.k);
@@ -224,7 +224,7 @@ struct OpXsph {
 struct OpBuildList {
     int* nbr; int* cnt;
     static constexpr bool kFluidOnly = false, kHi = false;
-    struct Acc { int n; };
+    struct Acc { int n; template <class F> __device__ void sums(F) {} };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.n = 0; }
     // layout: entries 4b..4b+3 of particle i form the int4 at nbr4[b * stride + i] (one coalesced LDG.128 per
     // batch of four neighbours in the walk)
@@ -349,6 +349,48 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, con
         walk_cells(s, op, acc, i, lo, m0);  // more neighbours than the list keeps: exact fallback
     }
     op.end(acc, i, lo, hi, s);
+}
+
+// Warp-cooperative list walk: FOUR lanes per particle, lane q takes list entries 4b+q, partial sums are combined
+// with two warp shuffles at the end.  A warp therefore covers 8 consecutive particles (one cell, or two):
+//   - the four indices of a batch of one particle are one int4, the 8 particles' int4s are 128 contiguous
+//     bytes: ONE fully coalesced line per warp request (was four);
+//   - at every step the 32 gathered records are neighbours of the SAME cell at the SAME list position, i.e. a
+//     few adjacent cache lines, instead of neighbours of four different cells (~13 lines): the L1 data pipe
+//     processes one line per wavefront, and its wavefront rate is what bounds these sweeps (ncu, profiles/).
+// The sums are formed as four interleaved partial sums (not the reference's sequential order): ~3e-7 relative.
+template <class Op>
+__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list4(const DevScene s, const Op op) {
+    const int t = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    const int q = t & 3;
+    int i = s.iBegin + (t >> 2);
+    const bool valid = i < s.iEnd;
+    if (!valid) i = s.iEnd - 1;                 // keep the quad convergent for the shuffles below
+    float4 lo, hi;
+    rec_full(s.rec + i, lo, hi);
+    const float3 xi = xyz(lo);
+    typename Op::Acc acc;
+    op.begin(acc, i, lo, hi, s);
+    const int n = s.cnt[i];
+    const float m0 = uniform_mass(s);
+    if (n <= s.kmax) {
+        const int nb4 = (n + 3) >> 2;
+        const size_t step = static_cast<size_t>(s.nbrStride) * 4;
+        const int* __restrict__ row = s.nbr + static_cast<size_t>(i) * 4 + q;
+        int jn = (nb4 > 0) ? __ldcs(row) : i;
+        for (int b = 0; b < nb4; ++b) {
+            const int j = jn;
+            row += step;
+            if (b + 1 < nb4) jn = __ldcs(row);
+            float4 l, h;
+            fetch<Op>(s, j, l, h);
+            list_pair(s, op, acc, i, xi, j, l, h, m0);
+        }
+    } else if (q == 0) {
+        walk_cells(s, op, acc, i, lo, m0);      // more neighbours than the list keeps: exact fallback on one lane
+    }
+    acc.sums([](float& v) { v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); });
+    if (valid && q == 0) op.end(acc, i, lo, hi, s);
 }
 
 // computeBoundaryMass_CUDA, SPHSystem.cu:79-105: boundary particles against the boundary set only
@@ -530,7 +572,8 @@ template <class Op> static int run_sweep(sphk_ctx* c, const sphk_scene* s, const
         const int rc = ensure_list(c, d);
         if (rc != SPHK_OK) return rc;
         d.nbr = c->nbr;
-        k_sweep_list<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
+        if (c->lanesPerParticle == 4) k_sweep_list4<Op><<<sphk_blocks(4 * (d.iEnd - d.iBegin)), SPHK_BLOCK, 0, c->stream>>>(d, op);
+        else k_sweep_list<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     } else {
         k_sweep_cells<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     }

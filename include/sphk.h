@@ -77,7 +77,10 @@ enum {
                                     27 cells (PBD moves positions inside a step, Q7).  default 1 */
     SPHK_OPT_LIST_CAPACITY = 2,  /* max neighbours kept per particle; particles with more fall back
                                     to the cell walk individually.  default 96 */
-    SPHK_OPT_TILE_SWEEP = 3      /* 1: cell-walk sweeps use the TMA-staged shared-memory tile kernel */
+    SPHK_OPT_TILE_SWEEP = 3,     /* 1: cell-walk sweeps use the TMA-staged shared-memory tile kernel */
+    SPHK_OPT_LANES_PER_PARTICLE = 4  /* list sweeps: 4 (default) = four lanes share a particle and split its
+                                    neighbours, partial sums combined by warp shuffles; 1 = thread per particle
+                                    (sums in the reference's sequential order) */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
