@@ -58,7 +58,7 @@ struct sphk_ctx {
     int actBegin = 0, actCount = -1; // active (owned) range of the sweeps; -1: all
     int kmax = 96;
     bool useList = true, useTile = false;
-    int lanesPerParticle = 4;        // list sweeps: 4 = warp-cooperative quad per particle, 1 = thread per particle
+    int lanesPerParticle = 1;        // list sweeps: 1 = thread per particle (default, faster on B200: profiles/), 4 = warp-cooperative quad
     unsigned long long searchEpoch = 0, listEpoch = ~0ull;
     bool posDirty = false;
     bool fluidSearched = false, boundarySearched = false, permValid = false;

@@ -78,9 +78,11 @@ enum {
     SPHK_OPT_LIST_CAPACITY = 2,  /* max neighbours kept per particle; particles with more fall back
                                     to the cell walk individually.  default 96 */
     SPHK_OPT_TILE_SWEEP = 3,     /* 1: cell-walk sweeps use the TMA-staged shared-memory tile kernel */
-    SPHK_OPT_LANES_PER_PARTICLE = 4  /* list sweeps: 4 (default) = four lanes share a particle and split its
-                                    neighbours, partial sums combined by warp shuffles; 1 = thread per particle
-                                    (sums in the reference's sequential order) */
+    SPHK_OPT_LANES_PER_PARTICLE = 4  /* list sweeps: 1 (default) = thread per particle, sums in the reference's
+                                    sequential order; 4 = four lanes share a particle and split its neighbours,
+                                    partial sums combined by warp shuffles (measured slower on B200: the sweeps
+                                    are bound by L1 sectors per gather, which lane cooperation does not reduce;
+                                    DESIGN.md) */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
