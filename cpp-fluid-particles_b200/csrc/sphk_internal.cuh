@@ -58,9 +58,13 @@ struct sphk_ctx {
     int actBegin = 0, actCount = -1; // active (owned) range of the sweeps; -1: all
     int kmax = 96;
     bool useList = true, useTile = false;
+    float skin = 0.f;                // neighbour-list skin as a fraction of R (PBD: positions move inside a step)
+    bool listHasSkin = false;        // the current list was built with a skin and displacement is being tracked
+    unsigned int* dispMax = nullptr; // device: max squared displacement since the list build (float bits)
     int lanesPerParticle = 1;        // list sweeps: 1 = thread per particle (default, faster on B200: profiles/), 4 = warp-cooperative quad
     unsigned long long searchEpoch = 0, listEpoch = ~0ull;
-    bool posDirty = false;
+    bool posDirty = false;           // positions changed since the last search
+    bool advected = false;           // ... by sphk_advect / sphk_refresh (not only by PBD corrections)
     bool fluidSearched = false, boundarySearched = false, permValid = false;
     const int* lastCsB = nullptr;
     long long launches = 0;
@@ -73,10 +77,14 @@ struct DevScene {
     const int* __restrict__ nbr;
     const int* __restrict__ cnt;
     const float* __restrict__ massRange;
+    const unsigned int* dispMax;     // non-null: skin list in use; fall back to the cell walk when *dispMax > dispLimit
+    unsigned int dispLimit;
+    float4* posBuild;                // positions at list build (skin lists)
     int nF, bOff, nbrStride, kmax;
     int iBegin, iEnd;                // sweeps compute particles [iBegin, iEnd)
     int3 cs, org;
     float cellLength;
+    float r2list;                    // candidate cut-off of the cell walk: r2cut, or (R + skin)^2 when building a skin list
     KConst k;
 };
 

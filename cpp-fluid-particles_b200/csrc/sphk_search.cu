@@ -194,6 +194,7 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
     if (e == cudaSuccess) e = dalloc(&c->snapB, cap);
     if (e == cudaSuccess) e = dalloc(&c->rec, tot);
     if (e == cudaSuccess) e = dalloc(&c->massRange, 2);
+    if (e == cudaSuccess) e = dalloc(&c->dispMax, 1);
     if (e == cudaSuccess) e = dalloc(&c->tmpF, 3 * static_cast<size_t>(max_fluid));
     if (e == cudaSuccess) e = dalloc(&c->partial, 1024);
     if (e == cudaSuccess) e = dalloc(&c->cnt, static_cast<size_t>(max_fluid));
@@ -212,7 +213,7 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
 extern "C" void sphk_destroy(sphk_ctx* c) {
     if (!c) return;
     cudaFree(c->keys); cudaFree(c->keysSorted); cudaFree(c->idx); cudaFree(c->idxSorted);
-    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec); cudaFree(c->massRange);
+    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec); cudaFree(c->massRange); cudaFree(c->dispMax);
     cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
@@ -230,6 +231,10 @@ extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
         }
         return SPHK_OK;
     case SPHK_OPT_TILE_SWEEP: c->useTile = value != 0; return SPHK_OK;
+    case SPHK_OPT_LIST_SKIN:
+        if (value < 0 || value > 1000) return SPHK_ERR_INVALID;
+        if (value * 0.001f != c->skin) { c->skin = value * 0.001f; c->listEpoch = ~0ull; }
+        return SPHK_OK;
     case SPHK_OPT_LANES_PER_PARTICLE:
         if (value != 1 && value != 4) return SPHK_ERR_INVALID;
         c->lanesPerParticle = value; return SPHK_OK;
@@ -287,7 +292,7 @@ extern "C" int sphk_neighbor_search(sphk_ctx* c, int which, const sphk_particles
                                                    c->rec + off, fluid ? 1 : 0, reinterpret_cast<unsigned int*>(c->massRange));
     k_cell_start<<<sphk_blocks(c->ncells + 1), SPHK_BLOCK, 0, st>>>(c->keysSorted, n, c->ncells, cell_start);
     c->launches += 3 + 4;   // 3 own kernels + CUB onesweep (histogram, scan, <=3 passes): counted as 4
-    if (fluid) { c->nF = n; c->fluidSearched = true; c->permValid = true; c->searchEpoch++; c->posDirty = false; c->sTag = nullptr;
+    if (fluid) { c->nF = n; c->fluidSearched = true; c->permValid = true; c->searchEpoch++; c->posDirty = false; c->advected = false; c->sTag = nullptr;
                  c->actBegin = 0; c->actCount = -1; }
     else { c->nB = n; c->boundarySearched = true; c->listEpoch = ~0ull; c->permValid = false; }
     SPHK_CUDA_TRY(cudaGetLastError());
@@ -313,6 +318,7 @@ extern "C" int sphk_refresh(sphk_ctx* c, const sphk_scene* s) {
                                                               reinterpret_cast<unsigned int*>(c->massRange));
     c->launches++;
     c->posDirty = true;
+    c->advected = true;
     c->sTag = nullptr;
     if (c->boundarySearched && s->boundary.pos && s->boundary.n == c->nB) {
         k_repack<<<sphk_blocks(c->nB), SPHK_BLOCK, 0, c->stream>>>(s->boundary.pos, nullptr, s->boundary.mass, c->nB,

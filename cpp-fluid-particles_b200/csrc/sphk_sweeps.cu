@@ -19,6 +19,7 @@
 // results agree with the reference kernels to ~1e-6 relative (tests/, <= 1e-5 required).
 // Compiled with -use_fast_math like the reference (Q10).
 #include <cstdio>
+#include <cstring>
 #include "sphk_internal.cuh"
 
 // =================================================================================================
@@ -222,7 +223,7 @@ struct OpXsph {
 // neighbour-list builder: keeps every candidate with r^2 <= r2cut in the cell walk's order, self excluded
 // (the self pair contributes exactly 0 to every operator: W(0)=0 by Q1, d = 0, v_i - v_i = 0).
 struct OpBuildList {
-    int* nbr; int* cnt;
+    int* nbr; int* cnt; float4* posBuild;
     static constexpr bool kFluidOnly = false, kHi = false;
     struct Acc { int n; template <class F> __device__ void sums(F) {} };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.n = 0; }
@@ -236,8 +237,9 @@ struct OpBuildList {
         if (a.n < s.kmax) nbr[slot(a.n, i, s)] = j;
         ++a.n;
     }
-    __device__ void end(Acc& a, int i, float4, float4, const DevScene& s) const {
+    __device__ void end(Acc& a, int i, float4 lo, float4, const DevScene& s) const {
         cnt[i] = a.n;
+        if (posBuild) posBuild[i] = lo;
         // pad the last batch with the particle itself: the self pair contributes exactly 0 to every operator
         for (int n = a.n; (n & 3) && n < s.kmax; ++n) nbr[slot(n, i, s)] = i;
     }
@@ -264,34 +266,44 @@ __device__ __forceinline__ float uniform_mass(const DevScene& s) {
     return (lo == hi) ? lo : -1.0f;
 }
 
+// The 27-cell walk, row-merged: the three z-neighbours (x+dx, y+dy, z-1..z+1) are consecutive cell indices,
+// hence ONE contiguous particle range per (dx,dy) row (CUDAFunctions.cuh:68: z is the fastest dimension).
+// Rows are visited in the reference's order (dx outermost); inside a row the fluid range comes first, then
+// the boundary range (the reference interleaves fluid/boundary per cell: the difference is the order of a few
+// boundary terms in the sum, ~1e-7 relative).  The centre cell is recomputed from the LIVE position while the
+// ranges stay those of the last search -- the reference's PBD semantics (Q7).
 template <class Op>
 __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float4 pi, float m0) {
     const int cx = cell_coord(pi.x, s.cellLength) - s.org.x, cy = cell_coord(pi.y, s.cellLength) - s.org.y,
               cz = cell_coord(pi.z, s.cellLength) - s.org.z;
     const float3 xi = xyz(pi);
+    if (cz < -1 || cz > s.cs.z) return;
+    const int zlo = max(cz - 1, 0), zhi = min(cz + 1, s.cs.z - 1);
+    if (zlo > zhi) return;
 #pragma unroll 1
-    for (int m = 0; m < 27; ++m) {
-        const int c = cell_index(cx + m / 9 - 1, cy + (m % 9) / 3 - 1, cz + m % 3 - 1, s.cs);
-        if (c == s.cs.x * s.cs.y * s.cs.z) continue;
+    for (int r = 0; r < 9; ++r) {
+        const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+        if (x < 0 || x >= s.cs.x || y < 0 || y >= s.cs.y) continue;
+        const int c0 = (x * s.cs.y + y) * s.cs.z;
         {
-            const int end = s.csF[c + 1];
-            for (int j = s.csF[c]; j < end; ++j) {
+            const int end = s.csF[c0 + zhi + 1];
+            for (int j = s.csF[c0 + zlo]; j < end; ++j) {
                 float4 lo, hi;
                 fetch<Op>(s, j, lo, hi);
                 const float3 d = xi - xyz(lo);
                 const float r2 = dot3(d, d);
-                if (r2 <= s.k.r2cut) op.pair(acc, i, j, false, d, r2, mass_of<Op>(s, j, false, hi, m0), lo, hi, s);
+                if (r2 <= s.r2list) op.pair(acc, i, j, false, d, r2, mass_of<Op>(s, j, false, hi, m0), lo, hi, s);
             }
         }
         if (!Op::kFluidOnly) {
-            const int end = s.csB[c + 1];
-            for (int jb = s.csB[c]; jb < end; ++jb) {
+            const int end = s.csB[c0 + zhi + 1];
+            for (int jb = s.csB[c0 + zlo]; jb < end; ++jb) {
                 const int j = s.bOff + jb;
                 float4 lo, hi;
                 fetch<Op>(s, j, lo, hi);
                 const float3 d = xi - xyz(lo);
                 const float r2 = dot3(d, d);
-                if (r2 <= s.k.r2cut) op.pair(acc, i, j, true, d, r2, mass_of<Op>(s, j, true, hi, m0), lo, hi, s);
+                if (r2 <= s.r2list) op.pair(acc, i, j, true, d, r2, mass_of<Op>(s, j, true, hi, m0), lo, hi, s);
             }
         }
     }
@@ -327,8 +339,9 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, con
     const float3 xi = xyz(lo);
     typename Op::Acc acc;
     op.begin(acc, i, lo, hi, s);
-    const int n = s.cnt[i];
+    int n = s.cnt[i];
     const float m0 = uniform_mass(s);
+    if (s.dispMax && *s.dispMax > s.dispLimit) n = s.kmax + 1;     // skin exhausted: everybody walks the cells
     if (n <= s.kmax) {
         const int nb4 = (n + 3) >> 2;
         const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + i;
@@ -371,8 +384,9 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list4(const DevScene s, co
     const float3 xi = xyz(lo);
     typename Op::Acc acc;
     op.begin(acc, i, lo, hi, s);
-    const int n = s.cnt[i];
+    int n = s.cnt[i];
     const float m0 = uniform_mass(s);
+    if (s.dispMax && *s.dispMax > s.dispLimit) n = s.kmax + 1;
     if (n <= s.kmax) {
         const int nb4 = (n + 3) >> 2;
         const size_t step = static_cast<size_t>(s.nbrStride) * 4;
@@ -473,14 +487,22 @@ k_advect(Rec* __restrict__ rec, float* __restrict__ pos, float* __restrict__ vel
 }
 // thrust::transform(pos += dpos) + enforceBoundary_CUDA(pos), PBDSolver.cu:212-223,247-253
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_apply_delta_pos(Rec* __restrict__ rec, float* __restrict__ pos, const float* __restrict__ dpos, int n, float3 space) {
+k_apply_delta_pos(Rec* __restrict__ rec, float* __restrict__ pos, const float* __restrict__ dpos, int n, float3 space,
+                  const float4* __restrict__ posBuild, unsigned int* __restrict__ dispMax) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= n) return;
-    float4 p = rec_lo(rec + i);
-    const float3 d = load3(dpos, i);
-    p.x += d.x; p.y += d.y; p.z += d.z;
-    clamp_axis(p.x, nullptr, space.x); clamp_axis(p.y, nullptr, space.y); clamp_axis(p.z, nullptr, space.z);
-    rec_set_pos(rec + i, xyz(p)); store3(pos, i, xyz(p));
+    float d2 = 0.f;
+    if (i < n) {
+        float4 p = rec_lo(rec + i);
+        const float3 d = load3(dpos, i);
+        p.x += d.x; p.y += d.y; p.z += d.z;
+        clamp_axis(p.x, nullptr, space.x); clamp_axis(p.y, nullptr, space.y); clamp_axis(p.z, nullptr, space.z);
+        rec_set_pos(rec + i, xyz(p)); store3(pos, i, xyz(p));
+        if (posBuild) { const float3 m = xyz(p) - xyz(posBuild[i]); d2 = dot3(m, m); }
+    }
+    if (posBuild) {     // max squared displacement since the (skin) list was built
+        for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+        if ((threadIdx.x & 31) == 0 && __float_as_uint(d2) > *dispMax) atomicMax(dispMax, __float_as_uint(d2));
+    }
 }
 // vel = (pos - posLast) / dt, PBDSolver.cu:55-60
 __global__ void __launch_bounds__(SPHK_BLOCK)
@@ -545,6 +567,8 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
     d.iBegin = c->actCount < 0 ? 0 : c->actBegin;
     d.iEnd = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
     d.k = kernel_constants(s->radius);
+    d.r2list = d.k.r2cut;
+    d.dispMax = nullptr; d.dispLimit = 0u; d.posBuild = nullptr;
     return d;
 }
 
@@ -557,7 +581,13 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
     DevScene b = d;
     b.nbr = c->nbr;
     b.iBegin = 0; b.iEnd = c->nF;       // lists are built for every local particle (ghosts included)
-    OpBuildList op{c->nbr, c->cnt};
+    c->listHasSkin = c->skin > 0.f;
+    if (c->listHasSkin) {
+        const float rs = d.k.R * (1.0f + c->skin);
+        b.r2list = rs * rs * (1.0f + 1e-5f);
+        if (cudaMemsetAsync(c->dispMax, 0, sizeof(unsigned int), c->stream) != cudaSuccess) return SPHK_ERR_STATE;
+    }
+    OpBuildList op{c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr};
     k_sweep_cells<OpBuildList><<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(b, op);
     c->launches++;
     c->listEpoch = c->searchEpoch;
@@ -567,11 +597,19 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
 template <class Op> static int run_sweep(sphk_ctx* c, const sphk_scene* s, const Op& op) {
     DevScene d = dev_scene(c, s);
     if (d.iEnd <= d.iBegin) return SPHK_OK;
-    const bool list = c->useList && !c->posDirty;
+    // the list is usable while positions are those of the search, or -- skin lists -- while the particles have
+    // only been moved by sphk_pbd_delta_pos_apply (displacement tracked on the device against skin/2)
+    const bool list = c->useList && (!c->posDirty || (c->skin > 0.f && !c->advected));
     if (list) {
         const int rc = ensure_list(c, d);
         if (rc != SPHK_OK) return rc;
         d.nbr = c->nbr;
+        if (c->listHasSkin) {
+            const float half = 0.5f * c->skin * d.k.R;
+            const float lim = half * half;
+            d.dispMax = c->dispMax;
+            memcpy(&d.dispLimit, &lim, sizeof(float));
+        }
         if (c->lanesPerParticle == 4) k_sweep_list4<Op><<<sphk_blocks(4 * (d.iEnd - d.iBegin)), SPHK_BLOCK, 0, c->stream>>>(d, op);
         else k_sweep_list<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     } else {
@@ -682,6 +720,7 @@ extern "C" int sphk_advect(sphk_ctx* c, const sphk_scene* s, float dt, const flo
                                                               make_float3(space[0], space[1], space[2]));
     c->launches++;
     c->posDirty = true;
+    c->advected = true;
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;
 }
@@ -747,8 +786,10 @@ extern "C" int sphk_pbd_delta_pos_apply(sphk_ctx* c, const sphk_scene* s, const 
     OpScalarGradient<2> op{c->rec, nullptr, delta_pos, rho0};
     const int rc = run_sweep(c, s, op);
     if (rc != SPHK_OK) return rc;
+    const bool track = c->listHasSkin && c->listEpoch == c->searchEpoch;
     k_apply_delta_pos<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(c->rec, s->fluid.pos, delta_pos, c->nF,
-                                                                       make_float3(space[0], space[1], space[2]));
+                                                                       make_float3(space[0], space[1], space[2]),
+                                                                       track ? c->snapA : nullptr, c->dispMax);
     c->launches++;
     c->posDirty = true;
     SPHK_CUDA_TRY(cudaGetLastError());
@@ -801,6 +842,15 @@ extern "C" int sphk_push_range(sphk_ctx* c, const sphk_scene* s, int what, const
     k_push_range<<<sphk_blocks(count), SPHK_BLOCK, 0, c->stream>>>(c->rec, (what & 1) ? s->fluid.vel : nullptr,
                                                                   (what & 2) ? array : nullptr, begin, count);
     c->launches++;
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+extern "C" int sphk_build_neighbor_list(sphk_ctx* c, const sphk_scene* s) {
+    SPHK_CHECK_SCENE(c, s);
+    const DevScene d = dev_scene(c, s);
+    const int rc = ensure_list(c, d);
+    if (rc != SPHK_OK) return rc;
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;
 }

@@ -102,8 +102,12 @@ class SphkOps:
     def _s(self):
         return C.byref(self.scene_abi())
 
-    def set_use_list(self, on: bool):
+    def set_use_list(self, on: bool, skin_permille: int = 0):
         check(self.L.sphk_set_option(self.ctx, capi.OPT_NEIGHBOR_LIST, 1 if on else 0))
+        check(self.L.sphk_set_option(self.ctx, capi.OPT_LIST_SKIN, int(skin_permille)))
+
+    def build_neighbor_list(self):
+        check(self.L.sphk_build_neighbor_list(self.ctx, self._s()), "sphk_build_neighbor_list")
 
     def search_boundary(self):
         p = self.boundary.abi()
@@ -275,7 +279,7 @@ class SphkOps:
             self.copy(self.pos_last, self.fluid.pos)
             self.pos_last_init = True
             return False
-        self.set_use_list(False)
+        self.set_use_list(self.use_list, 150 if self.use_list else 0)   # skin list: positions move inside the step
         self.permute(self.pos_last, 3)
         for _ in range(self.max_iter):
             self.pbd_density_lambda(); self.sync_scalar(self.lam)
@@ -345,7 +349,7 @@ class SphkSystem(SphkOps):
         if list_capacity is not None:
             check(self.L.sphk_set_option(self.ctx, capi.OPT_LIST_CAPACITY, int(list_capacity)))
         self.solver = self.p.solver
-        self.use_list = (self.solver != "pbd") if use_list is None else bool(use_list)
+        self.use_list = True if use_list is None else bool(use_list)
         n = self.fluid.n
         self._alloc_solver_buffers(n)
         self._scene = None

@@ -62,7 +62,7 @@ void Particles::advect(float dt) {
 // ================================================================================================
 bool BasicSPHSolver::beginStep(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
                                const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float radius,
-                               bool neighborList) {
+                               bool neighborList, int listSkinPermille) {
     const auto& eng = fluids->engine();
     if (!eng || !eng->ok()) {
         printf("SPH solver: particles are not bound to a B200 engine (construct them through SPHSystem)\n");
@@ -76,6 +76,7 @@ bool BasicSPHSolver::beginStep(std::shared_ptr<SPHParticles>& fluids, const std:
     current_.abi.cell_start_boundary = cellStartBoundary.addr();
     current_.abi.radius = radius;
     check(sphk_set_option(current_.ctx, SPHK_OPT_NEIGHBOR_LIST, neighborList ? 1 : 0), "sphk_set_option");
+    check(sphk_set_option(current_.ctx, SPHK_OPT_LIST_SKIN, listSkinPermille), "sphk_set_option");
     if (eng->shadowsStale) { check(sphk_refresh(current_.ctx, &current_.abi), "sphk_refresh"); eng->shadowsStale = false; }
     return true;
 }
@@ -85,7 +86,7 @@ void BasicSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shar
                           const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
                           int3 cellSize, float cellLength, float radius, float dt, float rho0, float rhoB, float stiff,
                           float visc, float3 G, float surfaceTensionIntensity, float airPressure) {
-    if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, true)) return;
+    if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, true, 0)) return;
     force(fluids, dt, G);
     diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, visc, dt);
     if (surfaceTensionIntensity > EPSILON || airPressure > EPSILON)
@@ -144,7 +145,7 @@ void DFSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_
                        const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
                        int3 cellSize, float cellLength, float radius, float dt, float rho0, float rhoB, float,
                        float visc, float3 G, float surfaceTensionIntensity, float airPressure) {
-    if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, true)) return;
+    if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, true, 0)) return;
     const int num = static_cast<int>(fluids->size());
     check(sphk_dfsph_density_alpha(current_.ctx, &current_.abi, alpha.addr()), "sphk_dfsph_density_alpha");
     itDiv_ = correctDivergenceError(rho0, dt, divergenceErrorThreshold, maxIter, num);
@@ -217,8 +218,9 @@ void PBDSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_pt
         initializePosLast(fluids->getPos());
         throw "PBD: The last position of fluids is initialized.";     // Q6, PBDSolver.cu:44-47
     }
-    // positions move inside the step (Q7): the per-step neighbour list does not apply
-    if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, false)) return;
+    // positions move inside the step (Q7): the neighbour list carries a skin of 0.15 R; the engine tracks the
+    // displacement on the device and falls back to the cell walk if the corrections ever exceed skin/2
+    if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, true, 150)) return;
     updateNeighborhood(fluids);
     project(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, cellSize, spaceSize, cellLength, radius, maxIter);
     check(sphk_pbd_velocity_from_positions(current_.ctx, &current_.abi, reinterpret_cast<float*>(fluidPosLast.addr()), dt),

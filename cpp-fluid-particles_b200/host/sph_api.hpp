@@ -188,7 +188,7 @@ protected:
     StepScene current_;
     bool beginStep(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
                    const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float radius,
-                   bool neighborList);
+                   bool neighborList, int listSkinPermille);
 private:
     DArray<float3> bufferFloat3;   // viscosity deltaV, then colour gradient (BasicSPHSolver.h:43)
 };

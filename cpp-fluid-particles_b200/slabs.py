@@ -226,7 +226,7 @@ class SlabSystem(SphkOps):
         check(self.L.sphk_create(C.byref(self.ctx), C.c_int(cap), C.c_int(self.boundary.n), C.byref(g),
                                  C.c_void_p(self.stream.cuda_stream)), "sphk_create")
         self._alloc_solver_buffers(cap)
-        self.use_list = self.solver != "pbd"
+        self.use_list = True
         self._scene = None
         self._G = (C.c_float * 3)(*[float(x) for x in p.gravity])
         self._space = (C.c_float * 3)(*[float(x) for x in p.space])

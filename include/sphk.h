@@ -78,6 +78,9 @@ enum {
     SPHK_OPT_LIST_CAPACITY = 2,  /* max neighbours kept per particle; particles with more fall back
                                     to the cell walk individually.  default 96 */
     SPHK_OPT_TILE_SWEEP = 3,     /* 1: cell-walk sweeps use the TMA-staged shared-memory tile kernel */
+    SPHK_OPT_LIST_SKIN = 5,      /* neighbour-list skin in 1/1000 of the radius (default 0).  With a skin the list
+                                    stays valid while sphk_pbd_delta_pos_apply moves particles by less than skin/2
+                                    (tracked on the device; beyond that every sweep falls back to the cell walk) */
     SPHK_OPT_LANES_PER_PARTICLE = 4  /* list sweeps: 1 (default) = thread per particle, sums in the reference's
                                     sequential order; 4 = four lanes share a particle and split its neighbours,
                                     partial sums combined by warp shuffles (measured slower on B200: the sweeps
@@ -171,6 +174,9 @@ int sphk_pbd_delta_pos_apply(sphk_ctx* ctx, const sphk_scene* s, const float* la
 int sphk_pbd_velocity_from_positions(sphk_ctx* ctx, const sphk_scene* s, const float* pos_last, float dt);
 /* XSPHViscosity_CUDA, PBDSolver.cu:89-125; Jacobi (the reference updates in place and races, Q5) */
 int sphk_pbd_xsph(sphk_ctx* ctx, const sphk_scene* s, float c, float rho0);
+
+/* Builds the per-step neighbour list now (sweeps otherwise build it lazily on first use). */
+int sphk_build_neighbor_list(sphk_ctx* ctx, const sphk_scene* s);
 
 /* ---- multi-GPU slab support (no reference counterpart: the reference is single-GPU) ----------------
  * A slab rank keeps [ghost-left | owned | ghost-right] particles in one sorted set (cpp-fluid-particles_b200/
