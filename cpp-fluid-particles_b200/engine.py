@@ -296,6 +296,9 @@ class SphkOps:
 
     def step(self):                  # SPHSystem.cu:129-158 (no host sync here; callers time with CUDA events)
         self.search_fluid()
+        if self.use_list:            # (the C++ layer builds the list lazily in the first sweep; same kernel)
+            self.set_use_list(True, 150 if self.solver == "pbd" else 0)
+            self.build_neighbor_list()
         if self.solver == "dfsph":
             self.step_dfsph()
         elif self.solver == "pbd":

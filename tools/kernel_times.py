@@ -7,4 +7,4 @@ if not line:
 d = json.loads(line[-1])
 print("ms/step %.3f  value %.1f M/s  e2e %.1f M/s  launches %d" % (d["ms_per_step"], d["value"] / 1e6, d["e2e"]["value"] / 1e6, d.get("gpu_launches", 0)))
 for k in d.get("roofline", {}).get("kernels", []):
-    print("  %-45s %.4f ms  %6.1f GB/s  share %.3f" % (k["kernel"], k["ms"], k["achieved_gbs"], k["share_of_step"]))
+    print("  %-50s %.4f ms  %8s GB/s  share %.3f" % (k["kernel"], k["ms"], "%.1f" % k["achieved_gbs"] if k["achieved_gbs"] else "-", k["share_of_step"]))
