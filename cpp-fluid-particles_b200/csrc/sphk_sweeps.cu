@@ -407,6 +407,85 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list4(const DevScene s, co
     if (valid && q == 0) op.end(acc, i, lo, hi, s);
 }
 
+// Dedicated neighbour-list builder (the generic k_sweep_cells<OpBuildList> is kept as the simple reference of
+// what it computes; tests compare the two).  Same candidate order as walk_cells, plus:
+//   - rows (dx,dy) whose cell rectangle is farther than the cut-off from the particle are skipped, and the
+//     z-extent of the others is trimmed to the cells the cut-off sphere can reach (conservative margins; a
+//     culled cell cannot contain a particle within the cut-off, so the list is unchanged);
+//   - candidates are fetched four at a time (independent LDG.128s in flight) and hits are buffered in
+//     registers and written as one 16-byte store per batch of four (coalesced across the warp) instead of
+//     four scattered 4-byte stores.
+struct ListSink {
+    int* nbr; int i, stride, kmax, n; int4 buf;
+    __device__ __forceinline__ void push(int j) {
+        switch (n & 3) { case 0: buf.x = j; break; case 1: buf.y = j; break; case 2: buf.z = j; break; default: buf.w = j; }
+        ++n;
+        if ((n & 3) == 0 && n <= kmax) reinterpret_cast<int4*>(nbr)[static_cast<size_t>((n >> 2) - 1) * stride + i] = buf;
+    }
+    __device__ __forceinline__ void finish() {       // pad the open batch with the particle itself (contributes 0)
+        if ((n & 3) != 0 && n < kmax) {
+            const int b = n >> 2;
+            if ((n & 3) <= 1) buf.y = i;
+            if ((n & 3) <= 2) buf.z = i;
+            buf.w = i;
+            reinterpret_cast<int4*>(nbr)[static_cast<size_t>(b) * stride + i] = buf;
+        }
+    }
+};
+
+__device__ __forceinline__ void build_range(const DevScene& s, ListSink& sink, float3 xi, int a, int b, int off) {
+    for (int j0 = a; j0 < b; j0 += 4) {
+        float4 p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = rec_lo(s.rec + off + min(j0 + k, b - 1));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float3 d = xi - xyz(p[k]);
+            const int j = off + j0 + k;
+            if (j0 + k < b && dot3(d, d) <= s.r2list && j != sink.i) sink.push(j);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_build_list(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, float4* __restrict__ posBuild) {
+    const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= s.nF) return;
+    const float4 lo = rec_lo(s.rec + i);
+    const float3 xi = xyz(lo);
+    ListSink sink{nbr, i, s.nbrStride, s.kmax, 0, make_int4(i, i, i, i)};
+    const int gx = cell_coord(lo.x, s.cellLength), gy = cell_coord(lo.y, s.cellLength), gz = cell_coord(lo.z, s.cellLength);
+    const int cx = gx - s.org.x, cy = gy - s.org.y, cz = gz - s.org.z;
+    const int zlo0 = max(cz - 1, 0), zhi0 = min(cz + 1, s.cs.z - 1);
+    if (zlo0 <= zhi0) {
+        const float cl = s.cellLength, margin = 1e-4f * cl;
+        const float rcut = sqrtf(s.r2list);
+#pragma unroll 1
+        for (int r = 0; r < 9; ++r) {
+            const int ox = r / 3 - 1, oy = r % 3 - 1;
+            const int x = cx + ox, y = cy + oy;
+            if (x < 0 || x >= s.cs.x || y < 0 || y >= s.cs.y) continue;
+            // distance from the particle to the (x,y) rectangle of the row's cells (global cell coordinates)
+            float ddx = 0.f, ddy = 0.f;
+            if (ox < 0) ddx = lo.x - gx * cl; else if (ox > 0) ddx = (gx + 1) * cl - lo.x;
+            if (oy < 0) ddy = lo.y - gy * cl; else if (oy > 0) ddy = (gy + 1) * cl - lo.y;
+            ddx = fmaxf(ddx - margin, 0.f); ddy = fmaxf(ddy - margin, 0.f);
+            const float rem = s.r2list - ddx * ddx - ddy * ddy;
+            if (rem < 0.f) continue;
+            const float ext = sqrtf(rem) + margin;
+            const int zlo = max(zlo0, cell_coord(lo.z - ext, cl) - s.org.z), zhi = min(zhi0, cell_coord(lo.z + ext, cl) - s.org.z);
+            if (zlo > zhi) continue;
+            (void)rcut;
+            const int c0 = (x * s.cs.y + y) * s.cs.z;
+            build_range(s, sink, xi, s.csF[c0 + zlo], s.csF[c0 + zhi + 1], 0);
+            build_range(s, sink, xi, s.csB[c0 + zlo], s.csB[c0 + zhi + 1], s.bOff);
+        }
+    }
+    sink.finish();
+    cnt[i] = sink.n;
+    if (posBuild) posBuild[i] = lo;
+}
+
 // computeBoundaryMass_CUDA, SPHSystem.cu:79-105: boundary particles against the boundary set only
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_boundary_mass(Rec* __restrict__ recB, float* __restrict__ mass, int n, const int* __restrict__ csB, int3 cs, int3 org,
@@ -587,8 +666,12 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
         b.r2list = rs * rs * (1.0f + 1e-5f);
         if (cudaMemsetAsync(c->dispMax, 0, sizeof(unsigned int), c->stream) != cudaSuccess) return SPHK_ERR_STATE;
     }
-    OpBuildList op{c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr};
-    k_sweep_cells<OpBuildList><<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(b, op);
+    if (c->simpleBuild) {
+        OpBuildList op{c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr};
+        k_sweep_cells<OpBuildList><<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(b, op);
+    } else {
+        k_build_list<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(b, c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr);
+    }
     c->launches++;
     c->listEpoch = c->searchEpoch;
     return SPHK_OK;
@@ -852,6 +935,17 @@ extern "C" int sphk_build_neighbor_list(sphk_ctx* c, const sphk_scene* s) {
     const int rc = ensure_list(c, d);
     if (rc != SPHK_OK) return rc;
     SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+extern "C" int sphk_get_neighbor_list(sphk_ctx* c, const sphk_scene* s, int* counts_out, int* entries_out) {
+    SPHK_CHECK_SCENE(c, s);
+    const DevScene d = dev_scene(c, s);
+    const int rc = ensure_list(c, d);
+    if (rc != SPHK_OK) return rc;
+    if (counts_out) SPHK_CUDA_TRY(cudaMemcpyAsync(counts_out, c->cnt, sizeof(int) * static_cast<size_t>(c->nF), cudaMemcpyDeviceToDevice, c->stream));
+    if (entries_out) SPHK_CUDA_TRY(cudaMemcpyAsync(entries_out, c->nbr, sizeof(int) * static_cast<size_t>(c->kmax) * c->capF,
+                                                   cudaMemcpyDeviceToDevice, c->stream));
     return SPHK_OK;
 }
 

@@ -137,6 +137,17 @@ class SphkOps:
         check(self.L.sphk_list_stats(self.ctx, self._s(), out))
         return {"max": int(out[0]), "overflow": int(out[1]), "total": int(out[2])}
 
+    def neighbor_list(self, capacity: int = 96):
+        """(counts[n], entries[capacity/4, cap, 4]) of the current list, as torch tensors."""
+        n, cap = self.fluid.n, self.fluid.pos.shape[0]
+        cnt = torch.zeros(n, dtype=torch.int32, device=self.device)
+        ent = torch.zeros(capacity * cap, dtype=torch.int32, device=self.device)
+        check(self.L.sphk_get_neighbor_list(self.ctx, self._s(), _ptr(cnt), _ptr(ent)))
+        return cnt, ent.view(capacity // 4, cap, 4)
+
+    def set_option(self, opt: int, value: int):
+        check(self.L.sphk_set_option(self.ctx, int(opt), int(value)))
+
     def launch_count(self) -> int:
         return int(self.L.sphk_launch_count(self.ctx))
 

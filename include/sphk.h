@@ -78,6 +78,7 @@ enum {
     SPHK_OPT_LIST_CAPACITY = 2,  /* max neighbours kept per particle; particles with more fall back
                                     to the cell walk individually.  default 96 */
     SPHK_OPT_TILE_SWEEP = 3,     /* 1: cell-walk sweeps use the TMA-staged shared-memory tile kernel */
+    SPHK_OPT_SIMPLE_LIST_BUILD = 6, /* 1: build the list with the generic cell walk (reference for the tuned builder) */
     SPHK_OPT_LIST_SKIN = 5,      /* neighbour-list skin in 1/1000 of the radius (default 0).  With a skin the list
                                     stays valid while sphk_pbd_delta_pos_apply moves particles by less than skin/2
                                     (tracked on the device; beyond that every sweep falls back to the cell walk) */
@@ -192,6 +193,9 @@ int sphk_push_range(sphk_ctx* ctx, const sphk_scene* s, int what, const float* a
 /* copies the stable-sort permutation of the last fluid search (perm[s] = pre-sort index) to device
  * memory `perm_out` (int[n]) */
 int sphk_get_permutation(sphk_ctx* ctx, int* perm_out, int n);
+/* raw copy of the current neighbour list (device to device): counts int[n]; entries int[capacity*max_fluid] in
+ * the int4-packed layout nbr4[(k/4)*max_fluid + i].{x,y,z,w}.  Either pointer may be NULL. */
+int sphk_get_neighbor_list(sphk_ctx* ctx, const sphk_scene* s, int* counts_out, int* entries_out);
 /* neighbour-list statistics of the last build: host ints {max_count, overflow_particles, total} */
 int sphk_list_stats(sphk_ctx* ctx, const sphk_scene* s, long long out_host[3]);
 

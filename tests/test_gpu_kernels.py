@@ -241,6 +241,29 @@ def test_permute_and_list_stats(pkg, built, O):
     s.close()
 
 
+@pytest.mark.parametrize("skin", [0, 150])
+def test_tuned_list_builder_equals_simple_cell_walk(pkg, built, O, skin):
+    """k_build_list (row culling, z trimming, batched loads, int4 stores) must produce exactly the list of the
+    generic cell walk: same counts, same entries in the same order, same self padding."""
+    torch = _torch()
+    from cpp_fluid_particles_b200 import capi
+    sc, s = _system(pkg, "config0", solver="dfsph", jitter=0.004)
+    lists = []
+    for simple in (1, 0):
+        s.set_option(capi.OPT_SIMPLE_LIST_BUILD, simple)
+        s.set_use_list(True, skin)
+        s.search_fluid()
+        cnt, ent = s.neighbor_list()
+        lists.append((cnt.cpu().numpy(), ent.cpu().numpy()))
+    (c0, e0), (c1, e1) = lists
+    assert np.array_equal(c0, c1) and c0.max() > 20
+    nb = (c0.max() + 3) // 4
+    k = np.arange(nb * 4).reshape(nb, 1, 4)
+    valid = k < (((c0 + 3) // 4) * 4)[None, :, None]          # entries incl. the self padding of the last batch
+    assert np.array_equal(np.where(valid, e0[:nb, :c0.shape[0]], -1), np.where(valid, e1[:nb, :c0.shape[0]], -1))
+    s.close()
+
+
 def test_list_overflow_falls_back_exactly(pkg, built, O):
     """A list capacity far below the neighbour count must not change results (per-particle cell-walk fallback)."""
     _torch()
