@@ -434,16 +434,10 @@ struct ListSink {
 };
 
 __device__ __forceinline__ void build_range(const DevScene& s, ListSink& sink, float3 xi, int a, int b, int off) {
-    for (int j0 = a; j0 < b; j0 += 4) {
-        float4 p[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) p[k] = rec_lo(s.rec + off + min(j0 + k, b - 1));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float3 d = xi - xyz(p[k]);
-            const int j = off + j0 + k;
-            if (j0 + k < b && dot3(d, d) <= s.r2list && j != sink.i) sink.push(j);
-        }
+#pragma unroll 4
+    for (int j = a; j < b; ++j) {
+        const float3 d = xi - xyz(rec_lo(s.rec + off + j));
+        if (dot3(d, d) <= s.r2list && off + j != sink.i) sink.push(off + j);
     }
 }
 
