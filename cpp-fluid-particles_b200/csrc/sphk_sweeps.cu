@@ -408,36 +408,33 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list4(const DevScene s, co
 }
 
 // Dedicated neighbour-list builder (the generic k_sweep_cells<OpBuildList> is kept as the simple reference of
-// what it computes; tests compare the two).  Same candidate order as walk_cells, plus:
-//   - rows (dx,dy) whose cell rectangle is farther than the cut-off from the particle are skipped, and the
-//     z-extent of the others is trimmed to the cells the cut-off sphere can reach (conservative margins; a
-//     culled cell cannot contain a particle within the cut-off, so the list is unchanged);
-//   - candidates are fetched four at a time (independent LDG.128s in flight) and hits are buffered in
-//     registers and written as one 16-byte store per batch of four (coalesced across the warp) instead of
-//     four scattered 4-byte stores.
-struct ListSink {
-    int* nbr; int i, stride, kmax, n; int4 buf;
-    __device__ __forceinline__ void push(int j) {
-        switch (n & 3) { case 0: buf.x = j; break; case 1: buf.y = j; break; case 2: buf.z = j; break; default: buf.w = j; }
-        ++n;
-        if ((n & 3) == 0 && n <= kmax) reinterpret_cast<int4*>(nbr)[static_cast<size_t>((n >> 2) - 1) * stride + i] = buf;
-    }
-    __device__ __forceinline__ void finish() {       // pad the open batch with the particle itself (contributes 0)
-        if ((n & 3) != 0 && n < kmax) {
-            const int b = n >> 2;
-            if ((n & 3) <= 1) buf.y = i;
-            if ((n & 3) <= 2) buf.z = i;
-            buf.w = i;
-            reinterpret_cast<int4*>(nbr)[static_cast<size_t>(b) * stride + i] = buf;
-        }
-    }
-};
-
-__device__ __forceinline__ void build_range(const DevScene& s, ListSink& sink, float3 xi, int a, int b, int off) {
+// what it computes; tests compare the two lists entry by entry).  Same candidate order as walk_cells.
+// The generic walk is issue-bound by SIMT divergence: ~15% of the candidates are hits, so with 32 lanes the
+// "append" path runs on almost every iteration at ~5/32 lane utilisation (ncu: 27 warp instructions per
+// candidate).  Here each chunk of <= 32 candidates is processed in two convergent phases:
+//   1. distance tests only, hits recorded as bits of a per-thread mask (no branches);
+//   2. the set bits are walked (find-first-set) and appended through a running pointer -- the trip count is
+//      the warp's maximum hit count (~7), not the candidate count.
+__device__ __forceinline__ void build_range(const DevScene& s, float3 xi, int i, int a, int b, int off, int& n, int*& wp,
+                                            long long jump) {
+    for (int j0 = a; j0 < b; j0 += 32) {
+        const int len = min(32, b - j0);
+        const Rec* base = s.rec + off + j0;
+        unsigned int mask = 0u;
 #pragma unroll 4
-    for (int j = a; j < b; ++j) {
-        const float3 d = xi - xyz(rec_lo(s.rec + off + j));
-        if (dot3(d, d) <= s.r2list && off + j != sink.i) sink.push(off + j);
+        for (int k = 0; k < len; ++k) {
+            const float3 d = xi - xyz(rec_lo(base + k));
+            mask |= (dot3(d, d) <= s.r2list ? 1u : 0u) << k;
+        }
+        const int self = i - (off + j0);
+        if (self >= 0 && self < 32) mask &= ~(1u << self);
+        while (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (n < s.kmax) *wp = off + j0 + k;
+            wp += ((n & 3) == 3) ? jump : 1;
+            ++n;
+        }
     }
 }
 
@@ -447,36 +444,25 @@ k_build_list(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, flo
     if (i >= s.nF) return;
     const float4 lo = rec_lo(s.rec + i);
     const float3 xi = xyz(lo);
-    ListSink sink{nbr, i, s.nbrStride, s.kmax, 0, make_int4(i, i, i, i)};
-    const int gx = cell_coord(lo.x, s.cellLength), gy = cell_coord(lo.y, s.cellLength), gz = cell_coord(lo.z, s.cellLength);
-    const int cx = gx - s.org.x, cy = gy - s.org.y, cz = gz - s.org.z;
-    const int zlo0 = max(cz - 1, 0), zhi0 = min(cz + 1, s.cs.z - 1);
-    if (zlo0 <= zhi0) {
-        const float cl = s.cellLength, margin = 1e-4f * cl;
-        const float rcut = sqrtf(s.r2list);
+    const int cx = cell_coord(lo.x, s.cellLength) - s.org.x, cy = cell_coord(lo.y, s.cellLength) - s.org.y,
+              cz = cell_coord(lo.z, s.cellLength) - s.org.z;
+    const int zlo = max(cz - 1, 0), zhi = min(cz + 1, s.cs.z - 1);
+    int n = 0;
+    int* wp = nbr + static_cast<size_t>(i) * 4;                       // slot of entry 0: nbr4[0 * stride + i].x
+    const long long jump = static_cast<long long>(s.nbrStride) * 4 - 3;  // from .w of batch b to .x of batch b+1
+    if (zlo <= zhi) {
 #pragma unroll 1
         for (int r = 0; r < 9; ++r) {
-            const int ox = r / 3 - 1, oy = r % 3 - 1;
-            const int x = cx + ox, y = cy + oy;
+            const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
             if (x < 0 || x >= s.cs.x || y < 0 || y >= s.cs.y) continue;
-            // distance from the particle to the (x,y) rectangle of the row's cells (global cell coordinates)
-            float ddx = 0.f, ddy = 0.f;
-            if (ox < 0) ddx = lo.x - gx * cl; else if (ox > 0) ddx = (gx + 1) * cl - lo.x;
-            if (oy < 0) ddy = lo.y - gy * cl; else if (oy > 0) ddy = (gy + 1) * cl - lo.y;
-            ddx = fmaxf(ddx - margin, 0.f); ddy = fmaxf(ddy - margin, 0.f);
-            const float rem = s.r2list - ddx * ddx - ddy * ddy;
-            if (rem < 0.f) continue;
-            const float ext = sqrtf(rem) + margin;
-            const int zlo = max(zlo0, cell_coord(lo.z - ext, cl) - s.org.z), zhi = min(zhi0, cell_coord(lo.z + ext, cl) - s.org.z);
-            if (zlo > zhi) continue;
-            (void)rcut;
             const int c0 = (x * s.cs.y + y) * s.cs.z;
-            build_range(s, sink, xi, s.csF[c0 + zlo], s.csF[c0 + zhi + 1], 0);
-            build_range(s, sink, xi, s.csB[c0 + zlo], s.csB[c0 + zhi + 1], s.bOff);
+            build_range(s, xi, i, s.csF[c0 + zlo], s.csF[c0 + zhi + 1], 0, n, wp, jump);
+            build_range(s, xi, i, s.csB[c0 + zlo], s.csB[c0 + zhi + 1], s.bOff, n, wp, jump);
         }
     }
-    sink.finish();
-    cnt[i] = sink.n;
+    cnt[i] = n;
+    // pad the open batch with the particle itself: the self pair contributes exactly 0 to every operator
+    for (int m = n; (m & 3) && m < s.kmax; ++m) { *wp = i; ++wp; }
     if (posBuild) posBuild[i] = lo;
 }
 
