@@ -131,44 +131,70 @@ class SlabExchange:
         return fl, fr
 
 
-def assemble_slab(ex: SlabExchange, rows: torch.Tensor, n_own: int, search, bounds):
-    """Steps A-D of the module docstring on a packed row tensor (one row per particle: pos, vel, history...).
+def assemble_slab(ex: SlabExchange, arrays, alt, offset: int, n_own: int, search, bounds):
+    """Steps A-D of the module docstring.
 
-    rows[:n_own]  owned particles (any order); rows has spare capacity behind them
-    search(n)     sorts rows[:n] by local cell key in place (stable) -- the engine's neighbour search
-    bounds()      host ints (s0, s1, s2, sw, sw1, send): offsets in the sorted array where local planes
-                  0, 1, 2, w, w+1 start and where plane w+1 ends (= number of in-grid particles);
-                  plane 0 / w+1 are the ghost planes, 1..w the owned ones
-    Returns (n_ghost_left, n_owned_new, n_ghost_right); rows[:total] = [ghostL | owned' | ghostR]."""
+    arrays   list of per-particle tensors (first dimension = particle slot, e.g. pos (cap,3), vel (cap,3),
+             history (cap,)); the owned particles occupy slots [offset, offset + n_own) in any order
+    alt      same-shaped scratch tensors (the result is assembled there, then the two sets are swapped in place)
+    search(offset, n)  sorts slots [offset, offset+n) of `arrays` by local cell key in place (stable)
+    bounds() host ints (s0, s1, s2, sw, sw1, send) RELATIVE to the searched slice: where local planes 0, 1, 2, w,
+             w+1 start and where plane w+1 ends (= number of in-grid particles); planes 0 / w+1 are the ghost
+             planes, 1..w the owned ones
+    On return arrays[:total] = [ghostL | stay | immigrants-from-left | immigrants-from-right | ghostR] (owned part
+    not yet sorted: the caller's final search sorts the whole set) and (n_ghost_left, n_owned_new, n_ghost_right)
+    is returned.
+
+    Ordering contract for the later field halos: the halo message of the first owned plane is
+    [stay particles of that plane (sorted), immigrants from the left]; both the sender's and the receiver's
+    final (stable) sorts see these particles in this relative order, so the sender's sorted first plane and the
+    receiver's sorted ghost plane are the same sequence (same for the last plane)."""
     # A. classify by sorting: particles that left the slab sit in the ghost planes, i.e. at the two ends
-    search(n_own)
+    search(offset, n_own)
     s0, s1, s2, sw, sw1, send = bounds()
     if s0 != 0 or send != n_own:
         raise RuntimeError(f"slab rank {ex.rank}: a particle moved more than one cell plane in one step "
                            f"({n_own - (send - s0)} of {n_own} outside the local grid); reduce dt or rebalance")
-    stay = rows[s1:sw1].clone()
-    # B. migrate
-    imm_l, imm_r = ex.exchange_rows(rows[0:s1].clone(), rows[sw1:n_own].clone())
-    n_new = stay.shape[0] + imm_l.shape[0] + imm_r.shape[0]
-    if n_new > rows.shape[0]:
-        raise RuntimeError(f"slab rank {ex.rank}: capacity {rows.shape[0]} exceeded by {n_new} owned particles")
-    rows[0:stay.shape[0]] = stay
-    rows[stay.shape[0]:stay.shape[0] + imm_l.shape[0]] = imm_l
-    rows[stay.shape[0] + imm_l.shape[0]:n_new] = imm_r
-    # C. sort owned': every particle must now lie in an owned plane
-    search(n_new)
-    s0, s1, s2, sw, sw1, send = bounds()
-    if s1 != 0 or sw1 != n_new or send != n_new:
-        raise RuntimeError(f"slab rank {ex.rank}: immigrants outside the owned planes")
-    # D. halo planes: first owned plane -> left neighbour, last owned plane -> right neighbour
-    gl, gr = ex.exchange_rows(rows[0:s2].clone(), rows[sw:n_new].clone())
+    widths = [1 if a.dim() == 1 else a.shape[1] for a in arrays]
+
+    def pack(lo, hi):                                   # rows [lo, hi) of the searched slice -> (m, sum(widths))
+        return torch.cat([a[offset + lo:offset + hi].reshape(hi - lo, w_) for a, w_ in zip(arrays, widths)], 1).contiguous()
+
+    def pieces(rows):
+        out, c = [], 0
+        for a, w in zip(arrays, widths):
+            out.append(rows[:, c:c + w].reshape((rows.shape[0],) + tuple(a.shape[1:])))
+            c += w
+        return out
+
+    # B. migrate (few particles): emigrants-left = plane 0, emigrants-right = plane w+1
+    imm_l, imm_r = ex.exchange_rows(pack(0, s1), pack(sw1, n_own))
+    n_stay = sw1 - s1
+    n_new = n_stay + imm_l.shape[0] + imm_r.shape[0]
+    # D. halo planes from stay + immigrants (no second sort): first owned plane -> left, last -> right
+    w_is_1 = (sw == s1)                                 # a one-plane slab: first plane == last plane
+    first = [pack(s1, s2), imm_l] + ([imm_r] if w_is_1 else [])
+    last = [pack(sw, sw1)] + ([imm_l] if w_is_1 else []) + [imm_r]
+    gl, gr = ex.exchange_rows(torch.cat(first, 0), torch.cat(last, 0))
     total = gl.shape[0] + n_new + gr.shape[0]
-    if total > rows.shape[0]:
-        raise RuntimeError(f"slab rank {ex.rank}: capacity {rows.shape[0]} exceeded by {total} local particles")
-    owned = rows[0:n_new].clone()
-    rows[0:gl.shape[0]] = gl
-    rows[gl.shape[0]:gl.shape[0] + n_new] = owned
-    rows[gl.shape[0] + n_new:total] = gr
+    cap = arrays[0].shape[0]
+    if total > cap:
+        raise RuntimeError(f"slab rank {ex.rank}: capacity {cap} exceeded by {total} local particles")
+    # assemble in the scratch set: [ghostL | stay | immL | immR | ghostR]
+    o = 0
+    for rows in (gl, None, imm_l, imm_r, gr):
+        if rows is None:
+            for a, d in zip(arrays, alt):
+                d[o:o + n_stay] = a[offset + s1:offset + sw1]
+            o += n_stay
+        else:
+            m = rows.shape[0]
+            if m:
+                for d, pc in zip(alt, pieces(rows)):
+                    d[o:o + m] = pc
+            o += m
+    for a, d in zip(arrays, alt):
+        a[:total] = d[:total]
     return gl.shape[0], n_new, gr.shape[0]
 
 
@@ -230,8 +256,6 @@ class SlabSystem(SphkOps):
         self._scene = None
         self._G = (C.c_float * 3)(*[float(x) for x in p.gravity])
         self._space = (C.c_float * 3)(*[float(x) for x in p.space])
-        self.hist = self.HISTORY[self.solver]
-        self.rows = torch.zeros((cap, 6 + self.hist), dtype=torch.float32, device=self.device)
         self.n_own, self.n_gl, self.n_gr = mine.shape[0], 0, 0
         # boundary: already in global sorted order -> identity permutation; masses given (not recomputed)
         # (the search's gather packs mass[s] of the sorted slot s into the records: the masses set above)
@@ -265,35 +289,28 @@ class SlabSystem(SphkOps):
         return pos, mass
 
     # ---- step ---------------------------------------------------------------------------------------------
-    def _pack_rows(self, n):
-        r = self.rows
-        r[:n, 0:3] = self.fluid.pos[:n]
-        r[:n, 3:6] = self.fluid.vel[:n]
+    def _carried(self):
+        """Per-particle arrays that migrate with a particle."""
+        arrs = [self.fluid.pos, self.fluid.vel]
         if self.solver == "dfsph":
-            r[:n, 6] = self.warm[:n]
+            arrs.append(self.warm)
         elif self.solver == "pbd":
-            r[:n, 6:9] = self.pos_last[:n]
+            arrs.append(self.pos_last)
+        return arrs
 
-    def _unpack_rows(self, n):
-        r = self.rows
-        self.fluid.pos[:n] = r[:n, 0:3]
-        self.fluid.vel[:n] = r[:n, 3:6]
+    def _search_slice(self, offset, n):
+        """search(offset, n) for assemble_slab: the C-ABI neighbour search on slots [offset, offset+n)."""
+        f = self.fluid
+        view = ParticleSet.__new__(ParticleSet)
+        view.n = n
+        view.pos, view.vel, view.mass = f.pos[offset:], f.vel[offset:], f.mass[offset:]
+        view.density, view.pressure, view.p2c = f.density[offset:], f.pressure[offset:], f.p2c[offset:]
+        p = view.abi()
+        check(self.L.sphk_neighbor_search(self.ctx, 0, C.byref(p), _ptr(self.cs_fluid)), "sphk_neighbor_search(f)")
         if self.solver == "dfsph":
-            self.warm[:n] = r[:n, 6]
+            check(self.L.sphk_permute(self.ctx, _ptr(self.warm[offset:]), C.c_int(1), C.c_int(n)), "sphk_permute")
         elif self.solver == "pbd":
-            self.pos_last[:n] = r[:n, 6:9]
-
-    def _search_rows(self, n):
-        """search(n) for assemble_slab: rows -> API arrays -> C-ABI neighbour search -> rows (sorted)."""
-        self._unpack_rows(n)
-        self.fluid.n = n
-        self._scene = None
-        self.search_fluid()
-        if self.solver == "dfsph":
-            self.permute(self.warm, 1)
-        elif self.solver == "pbd":
-            self.permute(self.pos_last, 3)
-        self._pack_rows(n)
+            check(self.L.sphk_permute(self.ctx, _ptr(self.pos_last[offset:]), C.c_int(3), C.c_int(n)), "sphk_permute")
 
     def _bounds(self):
         pc, w = self.plane_cells, self.w
@@ -302,25 +319,30 @@ class SlabSystem(SphkOps):
 
     def begin_step(self):
         t0 = time.perf_counter()
-        # drop last step's ghosts: owned particles to the front
-        if self.n_gl:
-            self.fluid.pos[:self.n_own] = self.fluid.pos[self.n_gl:self.n_gl + self.n_own].clone()
-            self.fluid.vel[:self.n_own] = self.fluid.vel[self.n_gl:self.n_gl + self.n_own].clone()
-            if self.solver == "dfsph":
-                self.warm[:self.n_own] = self.warm[self.n_gl:self.n_gl + self.n_own].clone()
-            elif self.solver == "pbd":
-                self.pos_last[:self.n_own] = self.pos_last[self.n_gl:self.n_gl + self.n_own].clone()
-        self._pack_rows(self.n_own)
-        self.n_gl, self.n_own, self.n_gr = assemble_slab(self.ex, self.rows, self.n_own, self._search_rows, self._bounds)
+        arrays = self._carried()
+        if not hasattr(self, "_alt"):
+            self._alt = [torch.empty_like(a) for a in arrays]
+        self.n_gl, self.n_own, self.n_gr = assemble_slab(self.ex, arrays, self._alt, self.n_gl, self.n_own,
+                                                         self._search_slice, self._bounds)
         n = self.n_gl + self.n_own + self.n_gr
-        self._search_rows(n)                             # E: identity permutation; ranges + records (+ list)
+        self.fluid.n = n
+        self._scene = None
+        self.search_fluid()                              # E: sorts [ghostL | owned' | ghostR]; ranges + records
+        if self.solver == "dfsph":
+            self.permute(self.warm, 1)
+        elif self.solver == "pbd":
+            self.permute(self.pos_last, 3)
         check(self.L.sphk_set_active_range(self.ctx, C.c_int(self.n_gl), C.c_int(self.n_own)))
         # owned first/last plane slices and ghost slices for the field syncs
         _, s1, s2, sw, sw1, _ = self._bounds()
+        assert s1 == self.n_gl and sw1 == self.n_gl + self.n_own, "ghost planes do not bracket the owned range"
         self.first_plane = (s1, s2)                      # [begin, end) in local arrays
         self.last_plane = (sw, sw1)
         self.ghost_l = (0, self.n_gl)
         self.ghost_r = (self.n_gl + self.n_own, n)
+        if self.use_list:
+            self.set_use_list(True, 0)
+            self.build_neighbor_list()
         self.comm_s += time.perf_counter() - t0
 
     # field syncs ------------------------------------------------------------------------------------------------

@@ -37,23 +37,25 @@ def _worker(rank, world, port, steps, q):
     ex = slabs.SlabExchange(rank, world, "cpu")
     mine = (plane >= x0) & (plane < x1)
     cap = n
-    rows = torch.zeros((cap, 7))
-    n_own = int(mine.sum())
-    rows[:n_own, 0:3] = torch.from_numpy(pos[mine]); rows[:n_own, 6] = torch.from_numpy(ids[mine])
+    P, V, ID = torch.zeros((cap, 3)), torch.zeros((cap, 3)), torch.zeros(cap)
+    alt = [torch.zeros((cap, 3)), torch.zeros((cap, 3)), torch.zeros(cap)]
+    n_own, gl = int(mine.sum()), 0
+    P[:n_own] = torch.from_numpy(pos[mine]); ID[:n_own] = torch.from_numpy(ids[mine])
     state = {}
 
-    def keys_of(r):
-        c = np.floor(r[:, 0:3].numpy()).astype(np.int64)
+    def keys_of(p):
+        c = np.floor(p.numpy()).astype(np.int64)
         lx = c[:, 0] - (x0 - 1)
         ok = (lx >= 0) & (lx < w + 2) & (c[:, 1] >= 0) & (c[:, 1] < CY) & (c[:, 2] >= 0) & (c[:, 2] < CZ)
         k = (lx * CY + c[:, 1]) * CZ + c[:, 2]
         return np.where(ok, k, (w + 2) * CY * CZ)
 
-    def search(m):                                        # stand-in for sphk_neighbor_search: stable sort by key
-        k = keys_of(rows[:m])
-        o = np.argsort(k, kind="stable")
-        rows[:m] = rows[:m][torch.from_numpy(o)]
-        state["keys"] = k[o]
+    def search(off, m):                                   # stand-in for sphk_neighbor_search: stable sort by key
+        k = keys_of(P[off:off + m])
+        o = torch.from_numpy(np.argsort(k, kind="stable"))
+        for a in (P, V, ID):
+            a[off:off + m] = a[off:off + m][o]
+        state["keys"] = k[o.numpy()]
 
     def bounds():
         pc = CY * CZ
@@ -61,34 +63,34 @@ def _worker(rank, world, port, steps, q):
 
     ok = True
     for step in range(steps):
-        # every rank moves the GLOBAL set identically (|dx| < 1 plane), and its own rows accordingly
+        # every rank moves the GLOBAL set identically (|dx| < 1 plane), and its own particles accordingly
         dx = rng.uniform(-0.45, 0.45, (n, 3)).astype(np.float32)
         dx[:, 1:] *= 0.2
         newpos = pos + dx
         newpos[:, 0] = np.clip(newpos[:, 0], 0.05, CX - 0.05)
         newpos[:, 1] = np.clip(newpos[:, 1], 0.01, CY - 0.01); newpos[:, 2] = np.clip(newpos[:, 2], 0.01, CZ - 0.01)
         pos = newpos
-        my_ids = rows[:n_own, 6].numpy().astype(np.int64)
-        rows[:n_own, 0:3] = torch.from_numpy(pos[my_ids])
-        gl, n_own, gr = slabs.assemble_slab(ex, rows, n_own, search, bounds)
+        my_ids = ID[gl:gl + n_own].numpy().astype(np.int64)
+        P[gl:gl + n_own] = torch.from_numpy(pos[my_ids])
+        gl, n_own, gr = slabs.assemble_slab(ex, [P, V, ID], alt, gl, n_own, search, bounds)
         total = gl + n_own + gr
-        search(total)                                     # step E: must be the identity
-        loc = rows[:total].numpy()
-        k = keys_of(rows[:total])
+        search(0, total)                                  # step E: the final sort of the assembled set
+        k = keys_of(P[:total])
         ok &= bool(np.all(np.diff(k) >= 0))
+        loc_ids = ID[:total].numpy().astype(np.int64)
         gplane = np.floor(pos[:, 0]).astype(np.int64)
-        own_ids = set(loc[gl:gl + n_own, 6].astype(np.int64).tolist())
-        ok &= own_ids == set(np.nonzero((gplane >= x0) & (gplane < x1))[0].tolist())
-        ok &= set(loc[:gl, 6].astype(np.int64).tolist()) == set(np.nonzero(gplane == x0 - 1)[0].tolist())
-        ok &= set(loc[gl + n_own:total, 6].astype(np.int64).tolist()) == set(np.nonzero(gplane == x1)[0].tolist())
-        ok &= bool(np.array_equal(loc[:, 0:3], pos[loc[:, 6].astype(np.int64)]))
-        # field halo: owners publish f = 2*id + step; ghosts must receive exactly that, in the ghost's order
+        ok &= set(loc_ids[gl:gl + n_own].tolist()) == set(np.nonzero((gplane >= x0) & (gplane < x1))[0].tolist())
+        ok &= set(loc_ids[:gl].tolist()) == set(np.nonzero(gplane == x0 - 1)[0].tolist())
+        ok &= set(loc_ids[gl + n_own:total].tolist()) == set(np.nonzero(gplane == x1)[0].tolist())
+        ok &= bool(np.array_equal(P[:total].numpy(), pos[loc_ids]))
+        # field halo: owners publish f = 2*id + step; ghosts must receive exactly that, in the ghost's SORTED order
+        # (this is the ordering contract of assemble_slab's docstring)
         f = torch.zeros(cap)
-        f[gl:gl + n_own] = 2 * rows[gl:gl + n_own, 6] + step
+        f[gl:gl + n_own] = 2 * ID[gl:gl + n_own] + step
         s0, s1, s2, sw, sw1, send = bounds()
+        ok &= (s1 == gl) and (sw1 == gl + n_own)
         ex.exchange(f[s1:s2].contiguous(), f[sw:sw1].contiguous(), f[0:gl], f[gl + n_own:total])
-        ok &= bool(torch.equal(f[:total], 2 * rows[:total, 6] + step))
-        rows[:n_own] = rows[gl:gl + n_own].clone()        # drop ghosts, like SlabSystem.begin_step
+        ok &= bool(torch.equal(f[:total], 2 * ID[:total] + step))
     allok = [None] * world
     dist.all_gather_object(allok, bool(ok))
     if rank == 0:
