@@ -245,6 +245,56 @@ struct OpBuildList {
     }
 };
 
+// Two operators in one sweep: every neighbour record is gathered once and fed to both.  Each operator keeps its
+// own accumulators and sees exactly the pairs it would see alone (a fluid-only operator is not shown boundary
+// neighbours), so each quantity is formed by the same operations in the same order as in its own sweep.
+template <class A, class B> struct OpPair {
+    A a; B b;
+    static constexpr bool kFluidOnly = A::kFluidOnly && B::kFluidOnly, kHi = A::kHi || B::kHi;
+    struct Acc {
+        typename A::Acc a; typename B::Acc b;
+        template <class F> __device__ void sums(F f) { a.sums(f); b.sums(f); }
+    };
+    __device__ void begin(Acc& c, int i, float4 lo, float4 hi, const DevScene& s) const { a.begin(c.a, i, lo, hi, s); b.begin(c.b, i, lo, hi, s); }
+    __device__ void pair(Acc& c, int i, int j, bool isB, float3 d, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
+        if (!(A::kFluidOnly && isB)) a.pair(c.a, i, j, isB, d, r2, mj, lo, hi, s);
+        if (!(B::kFluidOnly && isB)) b.pair(c.b, i, j, isB, d, r2, mj, lo, hi, s);
+    }
+    __device__ void end(Acc& c, int i, float4 lo, float4 hi, const DevScene& s) const { a.end(c.a, i, lo, hi, s); b.end(c.b, i, lo, hi, s); }
+};
+
+// viscosity + surface tension / air pressure in one sweep (BasicSPHSolver.cu:183-225 then :332-381): the
+// viscosity term reads the neighbours' velocity BEFORE either update (as both reference kernels do), the surface
+// term does not read velocities at all, so  v_new = (v + deltaV) + a_surf*dt  is the reference's sequence.
+struct OpViscositySurface {
+    float4* velNew; float* vel; float* deltaV; float rho0, visc, dt, kappa, airP;
+    static constexpr bool kFluidOnly = true, kHi = true;
+    struct Acc {
+        float3 av, as, vi; float cii, ratio;
+        template <class F> __device__ void sums(F f) { f(av.x); f(av.y); f(av.z); f(as.x); f(as.y); f(as.z); }
+    };
+    __device__ void begin(Acc& a, int, float4 lo, float4 hi, const DevScene&) const {
+        a.av = f3(0, 0, 0); a.as = f3(0, 0, 0); a.vi = xyz(hi);
+        a.cii = lo.w;
+        const float lci = sqrtf(lo.w);
+        a.ratio = lci / fmaxf(SPHK_EPS, lci);
+    }
+    __device__ void pair(Acc& a, int, int, bool, float3 d, float r2, float mj, float4 lo, float4 hi, const DevScene& s) const {
+        const float r = sqrtf(r2);
+        a.av += mj * ((xyz(hi) - a.vi) / rho0) * lap_visc(r, s.k);
+        const float mr = mj / (rho0 * rho0);
+        a.as += 0.25f * mr * kappa * (a.cii + lo.w) * (d * grad_st_factor(r, s.k));
+        a.as += airP * mr * (d * grad_w_factor(r, s.k)) * a.ratio;
+    }
+    __device__ void end(Acc& a, int i, float4, float4, const DevScene&) const {
+        const float3 dv = visc * a.av * dt;
+        store3(deltaV, i, dv);
+        float3 v = a.vi + dv;
+        v = f3(v.x + a.as.x * dt, v.y + a.as.y * dt, v.z + a.as.z * dt);
+        velNew[i] = make_float4(v.x, v.y, v.z, 0.f); store3(vel, i, v);
+    }
+};
+
 // =================================================================================================
 // Sweep drivers
 // =================================================================================================
@@ -904,6 +954,40 @@ extern "C" int sphk_push_range(sphk_ctx* c, const sphk_scene* s, int what, const
     if (count == 0) return SPHK_OK;
     k_push_range<<<sphk_blocks(count), SPHK_BLOCK, 0, c->stream>>>(c->rec, (what & 1) ? s->fluid.vel : nullptr,
                                                                   (what & 2) ? array : nullptr, begin, count);
+    c->launches++;
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+// ---- fused sweeps (same quantities, fewer passes over the neighbour lists) ------------------------------------
+extern "C" int sphk_fused_density_color_grad(sphk_ctx* c, const sphk_scene* s, float* color_grad, float rho0, float rhoB) {
+    SPHK_CHECK_SCENE(c, s);
+    if (!color_grad || !s->fluid.density) return SPHK_ERR_INVALID;
+    OpPair<OpDensity, OpColorGrad> op{OpDensity{s->fluid.density}, OpColorGrad{color_grad, rho0, rhoB}};
+    return run_sweep(c, s, op);
+}
+
+extern "C" int sphk_fused_dfsph_density_alpha_color_grad(sphk_ctx* c, const sphk_scene* s, float* alpha, float* color_grad,
+                                                        float rho0, float rhoB) {
+    SPHK_CHECK_SCENE(c, s);
+    if (!alpha || !color_grad || !s->fluid.density) return SPHK_ERR_INVALID;
+    OpPair<OpDensityAlpha, OpColorGrad> op{OpDensityAlpha{s->fluid.density, alpha}, OpColorGrad{color_grad, rho0, rhoB}};
+    return run_sweep(c, s, op);
+}
+
+extern "C" int sphk_fused_viscosity_surface(sphk_ctx* c, const sphk_scene* s, float* delta_v, const float* color_grad,
+                                            float rho0, float visc, float dt, float kappa, float airP) {
+    SPHK_CHECK_SCENE(c, s);
+    if (!delta_v || !color_grad || delta_v == color_grad) return SPHK_ERR_INVALID;
+    k_s_cg2<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(color_grad, c->rec, c->nF);
+    c->launches++;
+    c->sTag = nullptr;
+    float4* tmp = c->snapB;
+    OpViscositySurface op{tmp, s->fluid.vel, delta_v, rho0, visc, dt, kappa, airP};
+    const int rc = run_sweep(c, s, op);
+    if (rc != SPHK_OK) return rc;
+    const int b = c->actCount < 0 ? 0 : c->actBegin, e = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
+    if (e > b) k_commit_vel<<<sphk_blocks(e - b), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, nullptr, b, e);
     c->launches++;
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;

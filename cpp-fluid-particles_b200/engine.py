@@ -77,6 +77,8 @@ class SphkOps:
         dev = self.device
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
         self.buffer3 = f(n, 3)          # BasicSPHSolver::bufferFloat3
+        self.color_grad_buf = f(n, 3)   # second buffer: the fused viscosity+surface sweep needs deltaV and colour gradient at once
+        self.fused = True               # fused sweeps (default, like the C++ class layer) or one kernel per launch site
         if self.solver == "dfsph":      # DFSPHSolver.h:58-62
             self.alpha, self.kappa, self.error, self.warm = f(n), f(n), f(n), f(n)
             self.max_iter = self.p.max_iter if self.p.max_iter > 0 else 20
@@ -176,6 +178,21 @@ class SphkOps:
     def density(self):
         check(self.L.sphk_density(self.ctx, self._s()), "sphk_density")
 
+    def fused_density_color_grad(self, with_alpha: bool):
+        if with_alpha:
+            check(self.L.sphk_fused_dfsph_density_alpha_color_grad(self.ctx, self._s(), _ptr(self.alpha), _ptr(self.color_grad_buf),
+                                                                   C.c_float(self.p.rho0), C.c_float(self.p.rho_boundary)),
+                  "sphk_fused_dfsph_density_alpha_color_grad")
+        else:
+            check(self.L.sphk_fused_density_color_grad(self.ctx, self._s(), _ptr(self.color_grad_buf), C.c_float(self.p.rho0),
+                                                       C.c_float(self.p.rho_boundary)), "sphk_fused_density_color_grad")
+
+    def fused_viscosity_surface(self):
+        check(self.L.sphk_fused_viscosity_surface(self.ctx, self._s(), _ptr(self.buffer3), _ptr(self.color_grad_buf),
+                                                  C.c_float(self.p.rho0), C.c_float(self.p.visc), C.c_float(self.p.dt),
+                                                  C.c_float(self.p.surface_tension), C.c_float(self.p.air_pressure)),
+              "sphk_fused_viscosity_surface")
+
     def pressure(self):
         check(self.L.sphk_pressure(self.ctx, self._s(), C.c_float(self.p.rho0), C.c_float(self.p.stiff)), "sphk_pressure")
 
@@ -243,11 +260,15 @@ class SphkOps:
     def step_wcsph(self):            # BasicSPHSolver.cu:237-260
         self.set_use_list(self.use_list)
         self.gravity()
-        self.viscosity(); self.sync_vel()
-        if self._surface_enabled():  # handleSurface, :262-275
-            self.color_grad(); self.sync_array(self.buffer3)
-            self.surface(); self.sync_vel()
-        self.density()
+        if self.fused and self._surface_enabled():
+            self.fused_density_color_grad(False); self.sync_array(self.color_grad_buf)
+            self.fused_viscosity_surface(); self.sync_vel()
+        else:
+            self.viscosity(); self.sync_vel()
+            if self._surface_enabled():  # handleSurface, :262-275
+                self.color_grad(); self.sync_array(self.buffer3)
+                self.surface(); self.sync_vel()
+            self.density()
         self.pressure()
         self.sync_array(self.fluid.density); self.sync_array(self.fluid.pressure)
         self.pressure_force()
@@ -256,7 +277,11 @@ class SphkOps:
     def step_dfsph(self):            # DFSPHSolver.cu:33-72
         self.set_use_list(self.use_list)
         n, rho0 = self.n_total(), self.p.rho0
-        self.dfsph_density_alpha()
+        fused = self.fused and self._surface_enabled()
+        if fused:
+            self.fused_density_color_grad(True); self.sync_array(self.color_grad_buf)
+        else:
+            self.dfsph_density_alpha()
         total, it = 3.4e38, 0        # correctDivergenceError :331-363
         self.dfsph_div_error(); self.sync_scalar(self.kappa)
         while (it < 1 or total > self.div_thr * n * rho0) and it < self.max_iter:
@@ -267,10 +292,13 @@ class SphkOps:
                 total = self.reduce_sum(self.reduce_abs_sum(self.owned(self.error)))
         self.it_div = it
         self.gravity()
-        self.viscosity(); self.sync_vel()
-        if self._surface_enabled():
-            self.color_grad(); self.sync_array(self.buffer3)
-            self.surface(); self.sync_vel()
+        if fused:
+            self.fused_viscosity_surface(); self.sync_vel()
+        else:
+            self.viscosity(); self.sync_vel()
+            if self._surface_enabled():
+                self.color_grad(); self.sync_array(self.buffer3)
+                self.surface(); self.sync_vel()
         total, it = 3.4e38, 0        # project :160-210
         self.permute(self.warm, 1)
         self.dfsph_den_correct(self.warm); self.sync_vel()

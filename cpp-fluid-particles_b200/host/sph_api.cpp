@@ -87,13 +87,48 @@ void BasicSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shar
                           int3 cellSize, float cellLength, float radius, float dt, float rho0, float rhoB, float stiff,
                           float visc, float3 G, float surfaceTensionIntensity, float airPressure) {
     if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, true, 0)) return;
+    const bool surface = surfaceTensionIntensity > EPSILON || airPressure > EPSILON;
     force(fluids, dt, G);
-    diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, visc, dt);
-    if (surfaceTensionIntensity > EPSILON || airPressure > EPSILON)
-        handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
-                      dt, surfaceTensionIntensity, airPressure);
-    project(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, stiff, cellSize, cellLength, radius, dt);
+    if (fusedSweeps_) {
+        // density and the colour gradient depend on positions and masses only: one sweep computes both (the
+        // reference computes them in two sweeps, :277-330 and :32-83, with nothing in between that they read)
+        densityAndColorGrad(nullptr, rho0, rhoB, surface);
+        diffuseAndSurface(rho0, rhoB, visc, dt, surfaceTensionIntensity, airPressure, surface, true);
+        check(sphk_pressure(current_.ctx, &current_.abi, rho0, stiff), "sphk_pressure");
+        check(sphk_pressure_force(current_.ctx, &current_.abi, dt), "sphk_pressure_force");
+    } else {
+        diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, visc, dt);
+        if (surface)
+            handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
+                          dt, surfaceTensionIntensity, airPressure);
+        project(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, stiff, cellSize, cellLength, radius, dt);
+    }
     advect(fluids, dt, spaceSize);
+}
+
+void BasicSPHSolver::densityAndColorGrad(float* alphaOrNull, float rho0, float rhoB, bool surface) {
+    float* cg = reinterpret_cast<float*>(bufferColorGrad.addr());
+    if (alphaOrNull) {
+        if (surface) check(sphk_fused_dfsph_density_alpha_color_grad(current_.ctx, &current_.abi, alphaOrNull, cg, rho0, rhoB),
+                           "sphk_fused_dfsph_density_alpha_color_grad");
+        else check(sphk_dfsph_density_alpha(current_.ctx, &current_.abi, alphaOrNull), "sphk_dfsph_density_alpha");
+    } else {
+        if (surface) check(sphk_fused_density_color_grad(current_.ctx, &current_.abi, cg, rho0, rhoB), "sphk_fused_density_color_grad");
+        else check(sphk_density(current_.ctx, &current_.abi), "sphk_density");
+    }
+}
+
+void BasicSPHSolver::diffuseAndSurface(float rho0, float rhoB, float visc, float dt, float surfaceTensionIntensity,
+                                       float airPressure, bool surface, bool colorGradReady) {
+    float* dv = reinterpret_cast<float*>(bufferFloat3.addr());
+    float* cg = reinterpret_cast<float*>(bufferColorGrad.addr());
+    if (!surface) {
+        check(sphk_viscosity(current_.ctx, &current_.abi, dv, rho0, visc, dt), "sphk_viscosity");
+        return;
+    }
+    if (!colorGradReady) check(sphk_color_grad(current_.ctx, &current_.abi, cg, rho0, rhoB), "sphk_color_grad");
+    check(sphk_fused_viscosity_surface(current_.ctx, &current_.abi, dv, cg, rho0, visc, dt, surfaceTensionIntensity, airPressure),
+          "sphk_fused_viscosity_surface");
 }
 
 // :227-235
@@ -147,13 +182,19 @@ void DFSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_
                        float visc, float3 G, float surfaceTensionIntensity, float airPressure) {
     if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, true, 0)) return;
     const int num = static_cast<int>(fluids->size());
-    check(sphk_dfsph_density_alpha(current_.ctx, &current_.abi, alpha.addr()), "sphk_dfsph_density_alpha");
+    const bool surface = surfaceTensionIntensity > EPSILON || airPressure > EPSILON;
+    if (fusedSweeps_) densityAndColorGrad(alpha.addr(), rho0, rhoB, surface);   // colour gradient: positions only
+    else check(sphk_dfsph_density_alpha(current_.ctx, &current_.abi, alpha.addr()), "sphk_dfsph_density_alpha");
     itDiv_ = correctDivergenceError(rho0, dt, divergenceErrorThreshold, maxIter, num);
     force(fluids, dt, G);
-    BasicSPHSolver::diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, visc, dt);
-    if (surfaceTensionIntensity > EPSILON || airPressure > EPSILON)
-        handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
-                      dt, surfaceTensionIntensity, airPressure);
+    if (fusedSweeps_) {
+        diffuseAndSurface(rho0, rhoB, visc, dt, surfaceTensionIntensity, airPressure, surface, true);
+    } else {
+        BasicSPHSolver::diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, visc, dt);
+        if (surface)
+            handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
+                          dt, surfaceTensionIntensity, airPressure);
+    }
     itDen_ = project(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, cellSize, cellLength, radius, dt,
                      densityErrorThreshold, maxIter);
     advect(fluids, dt, spaceSize);

@@ -162,7 +162,9 @@ protected:
 // ---- BasicSPHSolver.h:20-51 (WCSPH; also the base of DFSPH and PBD) ----------------------------
 class BasicSPHSolver : public BaseSolver {
 public:
-    explicit BasicSPHSolver(int num) : bufferFloat3(num) {}
+    explicit BasicSPHSolver(int num) : bufferFloat3(num), bufferColorGrad(num) {}
+    // addition: false = one kernel per reference launch site (the per-op C-ABI path); true (default) = fused sweeps
+    void setFusedSweeps(bool on) { fusedSweeps_ = on; }
     virtual ~BasicSPHSolver() noexcept {}
     virtual void step(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
                       const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
@@ -186,11 +188,17 @@ protected:
         sphk_scene abi{};
     };
     StepScene current_;
+    // fused replacements of {computeDensity | computeDensityAlpha} + colour gradient, and viscosity + surface
+    void densityAndColorGrad(float* alphaOrNull, float rho0, float rhoB, bool surface);
+    void diffuseAndSurface(float rho0, float rhoB, float visc, float dt, float surfaceTensionIntensity, float airPressure,
+                           bool surface, bool colorGradReady);
+    bool fusedSweeps_ = true;
     bool beginStep(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
                    const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float radius,
                    bool neighborList, int listSkinPermille);
 private:
     DArray<float3> bufferFloat3;   // viscosity deltaV, then colour gradient (BasicSPHSolver.h:43)
+    DArray<float3> bufferColorGrad;   // addition: the fused viscosity+surface sweep needs both at once
 };
 
 // ---- DFSPHSolver.h:20-64 ----------------------------------------------------------------------

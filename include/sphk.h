@@ -145,6 +145,19 @@ int sphk_pressure_force(sphk_ctx* ctx, const sphk_scene* s, float dt);
 /* Particles::advect (Particles.cu:28-36) + enforceBoundary_CUDA(pos,vel) (BasicSPHSolver.cu:85-101) */
 int sphk_advect(sphk_ctx* ctx, const sphk_scene* s, float dt, const float space[3]);
 
+/* ---- fused sweeps: the same quantities as the per-launch-site entries above, computed in fewer passes over the
+ * neighbour lists (each neighbour record is gathered once for two operators).  Every quantity is formed by the
+ * same operations in the same order as in its own sweep.  The class layer uses these by default. */
+/* computeDensity_CUDA + computeColorGrad_CUDA (both depend on positions and masses only) */
+int sphk_fused_density_color_grad(sphk_ctx* ctx, const sphk_scene* s, float* color_grad, float rho0, float rho_boundary);
+/* computeDensityAlpha_CUDA + computeColorGrad_CUDA */
+int sphk_fused_dfsph_density_alpha_color_grad(sphk_ctx* ctx, const sphk_scene* s, float* alpha, float* color_grad,
+                                              float rho0, float rho_boundary);
+/* viscosity_CUDA (+ vel += deltaV) followed by surfaceTensionAndAirPressure_CUDA.  delta_v and color_grad must be
+ * distinct buffers (the reference reuses one buffer for both because it runs them one after the other). */
+int sphk_fused_viscosity_surface(sphk_ctx* ctx, const sphk_scene* s, float* delta_v, const float* color_grad,
+                                 float rho0, float visc, float dt, float surface_tension, float air_pressure);
+
 /* ---- DFSPH: DFSPHSolver.cu ----------------------------------------------------------------- */
 /* computeDensityAlpha_CUDA, DFSPHSolver.cu:212-259 */
 int sphk_dfsph_density_alpha(sphk_ctx* ctx, const sphk_scene* s, float* alpha);

@@ -154,6 +154,26 @@ def test_against_golden_fixtures(pkg, built, solver):
     app.close()
 
 
+@pytest.mark.parametrize("solver", ["wcsph", "dfsph"])
+def test_fused_sweeps_equal_per_launch_site_path(pkg, built, solver):
+    """The fused sweeps (default) against one kernel per reference launch site: same quantities, same order of
+    operations per quantity -> equal up to FMA contraction between kernel instantiations."""
+    _gpu()
+    from cpp_fluid_particles_b200 import engine
+    sc = pkg.scene.benchmark_scene("config0", solver)
+    a, b = engine.SphkSystem(sc, step0=False), engine.SphkSystem(sc, step0=False)
+    b.fused = False
+    for k in range(4):
+        a.step(); b.step()
+        sa, sb = a.state(), b.state()
+        assert np.array_equal(sa["p2c"], sb["p2c"])
+        assert_close(sa["pos"], sb["pos"], tol=1e-6, what=f"{solver} step {k} pos")
+        assert_close(sa["density"], sb["density"], tol=1e-6, what=f"{solver} step {k} density")
+        assert_close(sa["vel"], sb["vel"], tol=1e-5, what=f"{solver} step {k} vel")
+    assert a.launch_count() < b.launch_count()
+    a.close(); b.close()
+
+
 def test_dfsph_adaptive_iterations_run(pkg, built):
     """Default DFSPH (thresholds 1e-3, max 20; DFSPHSolver.h:27-30) uses the host-synchronising reduction:
     iteration counts are 'parity unpinned' (reduce order), so only sanity is asserted."""
