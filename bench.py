@@ -144,8 +144,7 @@ def run_reference(args, pkg) -> dict:
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0,
                                             "d2h_bytes_per_step": 0},
                 "config": {"workload": f"{solver} dam-break, CPU restatement (reference CUDA build unavailable here)"}}
-    if scene_name not in ("2m",):
-        scene_name = "2m"     # the reference is single-GPU: its arm always runs the 1-GPU scene
+    # the reference is single-GPU: at --gpus N its arm runs the SAME scene as this engine's N-GPU arm, on one B200
     sc = pkg.scene.benchmark_scene(scene_name, solver)
     n = sc.fluid.shape[0]
     app = capi.SphApp(sc, libref)
