@@ -107,7 +107,7 @@ def cpu_baseline(pkg, solver: str, budget_s: float = 25.0) -> dict:
     """The CPU restatement on a bounded sample of the workload: the same generator / constants / solver
     settings at the largest scene whose constructor (= step 0) + 1 step fit the budget."""
     from oracle import oracle as O
-    cores = O.num_threads()
+    cores = O.use_all_cores()
     best = None
     for name in ("config0", "200k", "2m"):
         sc = pkg.scene.benchmark_scene(name, solver)

@@ -64,6 +64,7 @@ struct sphk_ctx {
     unsigned int* dispMax = nullptr; // device: max squared displacement since the list build (float bits)
     int lanesPerParticle = 1;        // list sweeps: 1 = thread per particle (default, faster on B200: profiles/), 4 = warp-cooperative quad
     unsigned long long searchEpoch = 0, listEpoch = ~0ull;
+    int listBegin = 0, listEnd = 0;  // particle range the current list covers
     bool posDirty = false;           // positions changed since the last search
     bool advected = false;           // ... by sphk_advect / sphk_refresh (not only by PBD corrections)
     bool fluidSearched = false, boundarySearched = false, permValid = false;

@@ -490,8 +490,8 @@ __device__ __forceinline__ void build_range(const DevScene& s, float3 xi, int i,
 
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_build_list(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, float4* __restrict__ posBuild) {
-    const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= s.nF) return;
+    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= s.iEnd) return;
     const float4 lo = rec_lo(s.rec + i);
     const float3 xi = xyz(lo);
     const int cx = cell_coord(lo.x, s.cellLength) - s.org.x, cy = cell_coord(lo.y, s.cellLength) - s.org.y,
@@ -682,14 +682,15 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
 }
 
 static int ensure_list(sphk_ctx* c, const DevScene& d) {
-    if (c->listEpoch == c->searchEpoch) return SPHK_OK;
+    // lists are built for the particles the sweeps will compute (the active range: ghosts of a slab rank need none)
+    if (c->listEpoch == c->searchEpoch && d.iBegin >= c->listBegin && d.iEnd <= c->listEnd) return SPHK_OK;
     if (!c->nbr) {
         const size_t bytes = sizeof(int) * static_cast<size_t>(c->kmax) * static_cast<size_t>(c->capF);
         if (cudaMalloc(reinterpret_cast<void**>(&c->nbr), bytes) != cudaSuccess) { cudaGetLastError(); return SPHK_ERR_ALLOC; }
     }
     DevScene b = d;
     b.nbr = c->nbr;
-    b.iBegin = 0; b.iEnd = c->nF;       // lists are built for every local particle (ghosts included)
+    c->listBegin = d.iBegin; c->listEnd = d.iEnd;
     c->listHasSkin = c->skin > 0.f;
     if (c->listHasSkin) {
         const float rs = d.k.R * (1.0f + c->skin);
@@ -698,9 +699,9 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
     }
     if (c->simpleBuild) {
         OpBuildList op{c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr};
-        k_sweep_cells<OpBuildList><<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(b, op);
+        k_sweep_cells<OpBuildList><<<sphk_blocks(b.iEnd - b.iBegin), SPHK_BLOCK, 0, c->stream>>>(b, op);
     } else {
-        k_build_list<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(b, c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr);
+        k_build_list<<<sphk_blocks(b.iEnd - b.iBegin), SPHK_BLOCK, 0, c->stream>>>(b, c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr);
     }
     c->launches++;
     c->listEpoch = c->searchEpoch;
@@ -1021,7 +1022,7 @@ extern "C" int sphk_list_stats(sphk_ctx* c, const sphk_scene* s, long long out_h
     if (rc != SPHK_OK) return rc;
     unsigned long long* dev = reinterpret_cast<unsigned long long*>(c->partial);
     SPHK_CUDA_TRY(cudaMemsetAsync(dev, 0, 3 * sizeof(unsigned long long), c->stream));
-    k_list_stats<<<256, 256, 0, c->stream>>>(c->cnt, c->nF, c->kmax, dev);
+    k_list_stats<<<256, 256, 0, c->stream>>>(c->cnt + c->listBegin, c->listEnd - c->listBegin, c->kmax, dev);
     c->launches++;
     unsigned long long h[3];
     SPHK_CUDA_TRY(cudaMemcpyAsync(h, dev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

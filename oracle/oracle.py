@@ -243,5 +243,11 @@ class OracleSystem:
             pass
 
 
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
+    lib().oracle_set_num_threads(C.c_int(os.cpu_count() or 1))
+    return num_threads()
+
+
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
