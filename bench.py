@@ -43,6 +43,10 @@ ALG_BYTES = {  # algorithmic HBM bytes per fluid particl
     "density": 20, "density_alpha": 24, "pressure_force": 48, "viscosity": 40, "color_grad": 28, "surface": 52,
     "advect": 48, "dfsph_error": 44, "dfsph_correct": 44, "pbd_lambda": 24, "pbd_delta_pos": 32, "pbd_xsph": 40,
     "neighbor_search": 126,
+    # fused sweeps: the union of what the two operators read / write, shared reads counted once
+    "density_alpha+color_grad": 36,   # R pos12+mass4, W density4 alpha4 colorGrad12
+    "density+color_grad": 32,         # R pos12+mass4, W density4 colorGrad12
+    "viscosity+surface": 76,          # viscosity 40 + surface 52 - shared pos/mass 16
 }
 SCENE_OF_N = {1: "2m", 2: "4m", 4: "8m", 8: "16m"}
 
@@ -183,11 +187,15 @@ def workload_name(scene_name: str, solver: str) -> str:
 def timed_kernels(solver: str):
     """(label, method name on SphkSystem, algorithmic bytes key) of the sweeps timed individually."""
     if solver == "dfsph":
-        return [("density_alpha", "dfsph_density_alpha", "density_alpha"), ("dfsph_div_error", "dfsph_div_error", "dfsph_error"),
-                ("dfsph_div_correct", "dfsph_div_correct", "dfsph_correct")]
+        return [("density: computeDensityAlpha + colour gradient (fused sweep)", "fused_density_color_grad", "density_alpha+color_grad"),
+                ("dfsph_div_error", "dfsph_div_error", "dfsph_error"), ("dfsph_div_correct", "dfsph_div_correct", "dfsph_correct"),
+                ("dfsph_den_error", "dfsph_den_error", "dfsph_error"), ("dfsph_den_correct", "dfsph_den_correct", "dfsph_correct"),
+                ("viscosity + surface (fused sweep)", "fused_viscosity_surface", "viscosity+surface")]
     if solver == "pbd":
-        return [("pbd_density_lambda", "pbd_density_lambda", "pbd_lambda"), ("pbd_delta_pos_apply", "pbd_delta_pos_apply", "pbd_delta_pos")]
-    return [("density", "density", "density"), ("pressure_force", "pressure_force", "pressure_force")]
+        return [("density: pbd_density_lambda", "pbd_density_lambda", "pbd_lambda"),
+                ("pbd_delta_pos_apply", "pbd_delta_pos_apply", "pbd_delta_pos"), ("pbd_xsph", "pbd_xsph", "pbd_xsph")]
+    return [("density: computeDensity + colour gradient (fused sweep)", "fused_density_color_grad", "density+color_grad"),
+            ("pressure_force", "pressure_force", "pressure_force"), ("viscosity + surface (fused sweep)", "fused_viscosity_surface", "viscosity+surface")]
 
 
 def run_ours_single(args, pkg) -> dict:
