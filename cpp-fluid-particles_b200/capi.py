@@ -25,14 +25,14 @@ SPHK_FUNCTIONS = [
     "sphk_dfsph_den_error", "sphk_dfsph_den_correct", "sphk_reduce_abs_sum", "sphk_copy", "sphk_pbd_density_lambda",
     "sphk_pbd_delta_pos_apply", "sphk_pbd_velocity_from_positions", "sphk_pbd_xsph", "sphk_get_permutation",
     "sphk_list_stats", "sphk_set_active_range", "sphk_push_range", "sphk_build_neighbor_list", "sphk_get_neighbor_list", "sphk_fused_density_color_grad",
-    "sphk_fused_dfsph_density_alpha_color_grad", "sphk_fused_viscosity_surface",
+    "sphk_fused_dfsph_density_alpha_color_grad", "sphk_fused_viscosity_surface", "sphk_export_dots",
 ]
 SPH_APP_FUNCTIONS = [
     "sph_app_create", "sph_app_destroy", "sph_app_step", "sph_app_fluid_size", "sph_app_boundary_size",
     "sph_app_download_fluid", "sph_app_download_boundary", "sph_app_upload_fluid", "sph_app_engine",
 ]
 
-OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_TILE_SWEEP, OPT_LANES_PER_PARTICLE, OPT_LIST_SKIN, OPT_SIMPLE_LIST_BUILD = 1, 2, 3, 4, 5, 6
+OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_LANES_PER_PARTICLE, OPT_LIST_SKIN, OPT_SIMPLE_LIST_BUILD = 1, 2, 4, 5, 6
 
 
 class SphkGrid(C.Structure):

@@ -8,8 +8,8 @@
 //                        index, and a 16-byte-aligned float4 snapshot of pos / vel.
 //   2. cub::DeviceRadixSort::SortPairs on (key, index), only ceil(log2(ncells+1)) key bits
 //                        -> ONE stable sort of 8-byte pairs instead of two sorts of 16-byte pairs.
-//   3. k_gather        : one gather pass writes the sorted API float3 arrays and the packed float4
-//                        shadows (xyz+mass, vel) the sweep kernels read with single LDG.128s.
+//   3. k_gather        : one gather pass writes the sorted API float3 arrays and the packed 32-byte
+//                        records {x,y,z,s | vx,vy,vz,m} the sweep kernels gather (one sector per neighbour).
 //   4. k_cell_start    : cell_start[c] = lower_bound(sortedKeys, c) -- no atomics, no scan, equals
 //                        fill + countingInCell_CUDA + exclusive_scan (SPHSystem.cu:123-125) exactly.
 // HBM-bound; algorithmic bytes per particle are listed in DESIGN.md.
@@ -230,7 +230,6 @@ extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
             c->kmax = value; c->listEpoch = ~0ull;
         }
         return SPHK_OK;
-    case SPHK_OPT_TILE_SWEEP: c->useTile = value != 0; return SPHK_OK;
     case SPHK_OPT_SIMPLE_LIST_BUILD: c->simpleBuild = value != 0; c->listEpoch = ~0ull; return SPHK_OK;
     case SPHK_OPT_LIST_SKIN:
         if (value < 0 || value > 1000) return SPHK_ERR_INVALID;
@@ -360,6 +359,30 @@ extern "C" int sphk_reduce_abs_sum(sphk_ctx* c, const float* x, int n, float* ho
     SPHK_CUDA_TRY(cudaMemcpyAsync(c->pinned, c->partial, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     SPHK_CUDA_TRY(cudaStreamSynchronize(c->stream));
     *host_out = *c->pinned;
+    return SPHK_OK;
+}
+
+// generate_dots_CUDA, vbo.cu:26-44
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_export_dots(const float* __restrict__ pos, const float* __restrict__ density, float* __restrict__ dot, float* __restrict__ color, int n) {
+    const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    store3(dot, i, load3(pos, i));
+    const float d = density[i];
+    const float3 blue = f3(0.34f, 0.46f, 0.7f), white = f3(0.9f, 0.9f, 0.9f), pink = f3(1.0f, 0.4f, 0.7f);
+    float3 c;
+    if (d < 0.75f) c = blue;
+    else if (d < 1.0f) { const float w = (d - 0.75f) * 4.0f; c = w * white + (1 - w) * blue; }
+    else { float w = (powf(d, 2) - 1.0f) * 4.0f; w = fminf(w, 1.0f); c = (1 - w) * white + w * pink; }
+    store3(color, i, c);
+}
+
+extern "C" int sphk_export_dots(sphk_ctx* c, const sphk_particles* p, float* dot, float* color) {
+    if (!c || !p || !p->pos || !p->density || !dot || !color || p->n < 0) return SPHK_ERR_INVALID;
+    if (p->n > 0) k_export_dots<<<sphk_blocks(p->n), SPHK_BLOCK, 0, c->stream>>>(p->pos, p->density, dot, color, p->n);
+    c->launches++;
+    SPHK_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;
 }
 

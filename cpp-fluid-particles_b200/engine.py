@@ -150,6 +150,15 @@ class SphkOps:
     def set_option(self, opt: int, value: int):
         check(self.L.sphk_set_option(self.ctx, int(opt), int(value)))
 
+    def export_dots(self):
+        """generate_dots (vbo.cu:26-51): (dot, colour) device tensors for the fluid set."""
+        n = self.fluid.n
+        dot = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        col = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        p = self.fluid.abi()
+        check(self.L.sphk_export_dots(self.ctx, C.byref(p), _ptr(dot), _ptr(col)), "sphk_export_dots")
+        return dot, col
+
     def launch_count(self) -> int:
         return int(self.L.sphk_launch_count(self.ctx))
 

@@ -380,3 +380,11 @@ float SPHSystem::step() {
     CUDA_CALL(cudaEventElapsedTime(&milliseconds, _evStart, _evStop));
     return milliseconds;
 }
+
+// vbo.cu:46-51
+extern "C" void generate_dots(float3* dot, float3* color, const std::shared_ptr<SPHParticles> particles) {
+    const auto& eng = particles->engine();
+    if (!eng || !eng->ok()) { printf("generate_dots: particles are not bound to a B200 engine\n"); return; }
+    const sphk_particles p = particles->abi();
+    check(sphk_export_dots(eng->ctx(), &p, reinterpret_cast<float*>(dot), reinterpret_cast<float*>(color)), "sphk_export_dots");
+}

@@ -324,3 +324,8 @@ private:
     void computeBoundaryMass();
     void neighborSearch(const std::shared_ptr<SPHParticles>& particles, DArray<int>& cellStart);
 };
+
+// ---- vbo.cu:46-51 --------------------------------------------------------------------------------
+// Same signature and linkage as the reference's render hook; writes plain device buffers (the reference maps a GL
+// vertex buffer and passes its device pointers: the call site main.cpp:268-281 is unchanged).
+extern "C" void generate_dots(float3* dot, float3* color, const std::shared_ptr<SPHParticles> particles);

@@ -16,12 +16,14 @@
  *  - All work is enqueued on the stream given to sphk_create (a cudaStream_t passed as void*).
  *  - There is NO CPU fallback: without a CUDA device sphk_create fails with SPHK_ERR_NO_DEVICE.
  *  - The library never allocates or frees API-visible arrays; sphk_ctx owns only scratch (sort
- *    buffers, packed float4 shadows of the particle attributes, neighbour lists).
+ *    buffers, packed 32-byte particle records, neighbour lists).
  *
- * Shadow coherence rule: sphk_neighbor_search() packs the particle set into float4 shadows that the
- * sweep kernels read; every sphk_* call that changes pos / vel writes both the API array and the
- * shadow.  If the caller edits pos / vel itself between calls it must call sphk_neighbor_search (or
- * sphk_refresh) before the next sweep.
+ * Record coherence rule: sphk_neighbor_search() packs the particle set into 32-byte records
+ * {x,y,z,s | vx,vy,vz,m} that the sweep kernels gather; every sphk_* call that changes pos / vel writes
+ * both the API array and the record.  If the caller edits pos / vel itself between calls it must call
+ * sphk_neighbor_search (or sphk_refresh) before the next sweep.  A scalar array passed to a sweep that
+ * gathers it from neighbours (stiffness, lambda) is mirrored into the records unless the previous sphk_*
+ * call produced it; arrays modified behind the library's back need sphk_refresh.
  */
 #ifndef SPHK_H_
 #define SPHK_H_
@@ -74,10 +76,9 @@ typedef struct sphk_scene {
 enum {
     SPHK_OPT_NEIGHBOR_LIST = 1,  /* 1: sweeps walk a per-step neighbour list while positions are
                                     unchanged since the search (WCSPH, DFSPH); 0: always walk the
-                                    27 cells (PBD moves positions inside a step, Q7).  default 1 */
+                                    27 cells.  default 1 */
     SPHK_OPT_LIST_CAPACITY = 2,  /* max neighbours kept per particle; particles with more fall back
                                     to the cell walk individually.  default 96 */
-    SPHK_OPT_TILE_SWEEP = 3,     /* 1: cell-walk sweeps use the TMA-staged shared-memory tile kernel */
     SPHK_OPT_SIMPLE_LIST_BUILD = 6, /* 1: build the list with the generic cell walk (reference for the tuned builder) */
     SPHK_OPT_LIST_SKIN = 5,      /* neighbour-list skin in 1/1000 of the radius (default 0).  With a skin the list
                                     stays valid while sphk_pbd_delta_pos_apply moves particles by less than skin/2
@@ -191,6 +192,11 @@ int sphk_pbd_xsph(sphk_ctx* ctx, const sphk_scene* s, float c, float rho0);
 
 /* Builds the per-step neighbour list now (sweeps otherwise build it lazily on first use). */
 int sphk_build_neighbor_list(sphk_ctx* ctx, const sphk_scene* s);
+
+/* ---- render export: generate_dots_CUDA, vbo.cu:26-44 -----------------------------------------------
+ * dot[i] = pos[i]; colour[i] from density[i] (blue below 0.75, blend to white at 1.0, blend to pink above).  Plain
+ * device buffers instead of a mapped GL vertex buffer; synchronises like the reference (vbo.cu:49). */
+int sphk_export_dots(sphk_ctx* ctx, const sphk_particles* p, float* dot_xyz, float* color_rgb);
 
 /* ---- multi-GPU slab support (no reference counterpart: the reference is single-GPU) ----------------
  * A slab rank keeps [ghost-left | owned | ghost-right] particles in one sorted set (cpp-fluid-particles_b200/

@@ -195,6 +195,13 @@ def pbd_xsph(sc, vel, c, rho0):
     return out
 
 
+def export_dots(pos, dens):
+    pos, dens = f32(pos), f32(dens)
+    dot, col = np.zeros_like(pos), np.zeros_like(pos)
+    lib().oracle_export_dots(_p(pos), _p(dens), C.c_int(pos.shape[0]), _p(dot), _p(col))
+    return dot, col
+
+
 # ---- whole system -----------------------------------------------------------------------------
 _FIELDS = {"pos": (0, 3, np.float32), "vel": (1, 3, np.float32), "mass": (2, 1, np.float32),
            "density": (3, 1, np.float32), "pressure": (4, 1, np.float32), "p2c": (5, 1, np.int32),

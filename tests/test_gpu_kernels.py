@@ -281,6 +281,20 @@ def test_list_overflow_falls_back_exactly(pkg, built, O):
     s.close(); s2.close()
 
 
+def test_export_dots_vs_oracle(pkg, built, O):
+    """generate_dots_CUDA (vbo.cu:26-44): positions copied, colour ramp of the density, all three branches."""
+    torch = _torch()
+    sc, s = _system(pkg, "mini", solver="wcsph", jitter=0.003)
+    n = s.fluid.n
+    dens = np.linspace(0.5, 1.3, n).astype(np.float32)
+    s.fluid.density.copy_(torch.from_numpy(dens))
+    dot, col = s.export_dots()
+    rd, rc = O.export_dots(s.fluid.pos.cpu().numpy(), dens)
+    assert np.array_equal(bits(dot.cpu().numpy()), bits(rd))
+    assert_close(col.cpu().numpy(), rc, tol=1e-6, what="dot colours")
+    s.close()
+
+
 def test_errors_are_reported_not_thrown(pkg, built):
     """C-ABI error behaviour: bad arguments / bad call order return codes, never crash."""
     import ctypes as C

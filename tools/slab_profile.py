@@ -17,6 +17,17 @@ s = slabs.SlabSystem(sc, rank, world, torch.device("cuda", local))
 for _ in range(3):
     s.step()
 ev = lambda: torch.cuda.Event(enable_timing=True)
+# finer split of begin_step: wrap the pieces
+import time as _t
+marks = {}
+def wrap(obj, name, label):
+    inner = getattr(obj, name)
+    def f(*a, **k):
+        e0, e1 = ev(), ev(); e0.record(); t0 = _t.perf_counter(); r = inner(*a, **k); dt = _t.perf_counter() - t0; e1.record()
+        marks.setdefault(label, []).append((e0, e1, dt)); return r
+    setattr(obj, name, f)
+wrap(s, "_search_slice", "searchA"); wrap(s, "search_fluid", "searchE"); wrap(s, "build_neighbor_list", "build")
+wrap(s.ex, "exchange_rows", "exchange_rows"); wrap(s, "_bounds", "bounds(sync)"); wrap(s.ex, "exchange", "field_sync")
 tb, ts = 0.0, 0.0
 K = 10
 for _ in range(K):
@@ -25,5 +36,8 @@ for _ in range(K):
     torch.cuda.synchronize()
     tb += e0.elapsed_time(e1); ts += e1.elapsed_time(e2)
 if rank == 0:
+    for k, v in marks.items():
+        v = v[-K * max(1, len(v) // (K + 3)):]
+        print(f"   {k:16s} calls/step {len(v)/K:5.1f}  gpu {sum(a.elapsed_time(b) for a, b, _ in v)/K:7.3f} ms/step  host {sum(d for _, _, d in v)/K*1e3:7.3f} ms/step")
     print(f"world {world} scene {scene}: begin_step {tb/K:.3f} ms  solver {ts/K:.3f} ms  (n_own {s.n_own}, ghosts {s.n_gl}+{s.n_gr})", flush=True)
 s.close(); dist.barrier(); dist.destroy_process_group()
