@@ -980,9 +980,14 @@ extern "C" int sphk_fused_viscosity_surface(sphk_ctx* c, const sphk_scene* s, fl
                                             float rho0, float visc, float dt, float kappa, float airP) {
     SPHK_CHECK_SCENE(c, s);
     if (!delta_v || !color_grad || delta_v == color_grad) return SPHK_ERR_INVALID;
-    k_s_cg2<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(color_grad, c->rec, c->nF);
-    c->launches++;
-    c->sTag = nullptr;
+    // rec.s <- |colour gradient|^2 (tagged with the array address | 1 so that repeated calls on sub-ranges of one
+    // sweep -- the slab driver computes the boundary planes first -- do not redo the pre-pass)
+    const void* tag = reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(color_grad) | 1u);
+    if (c->sTag != tag) {
+        k_s_cg2<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(color_grad, c->rec, c->nF);
+        c->launches++;
+        c->sTag = tag;
+    }
     float4* tmp = c->snapB;
     OpViscositySurface op{tmp, s->fluid.vel, delta_v, rho0, visc, dt, kappa, airP};
     const int rc = run_sweep(c, s, op);

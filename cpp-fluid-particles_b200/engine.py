@@ -266,17 +266,29 @@ class SphkOps:
             self.color_grad()
             self.surface()
 
+    def _run(self, op, sync=None, tensor=None, split=True):
+        """One sweep followed by the halo refresh of what it produced (`sync`: None | "vel" | "scalar" | "array").
+        On one GPU the refresh is a no-op; the slab driver overrides this to overlap the exchange with the sweep
+        (split=False: the sweep reads the field it writes -- Jacobi velocity updates -- and must run in one piece)."""
+        op()
+        if sync == "vel":
+            self.sync_vel()
+        elif sync == "scalar":
+            self.sync_scalar(tensor)
+        elif sync == "array":
+            self.sync_array(tensor)
+
     def step_wcsph(self):            # BasicSPHSolver.cu:237-260
         self.set_use_list(self.use_list)
         self.gravity()
         if self.fused and self._surface_enabled():
-            self.fused_density_color_grad(False); self.sync_array(self.color_grad_buf)
-            self.fused_viscosity_surface(); self.sync_vel()
+            self._run(lambda: self.fused_density_color_grad(False), "array", self.color_grad_buf)
+            self._run(self.fused_viscosity_surface, "vel", split=False)
         else:
-            self.viscosity(); self.sync_vel()
+            self._run(self.viscosity, "vel", split=False)
             if self._surface_enabled():  # handleSurface, :262-275
-                self.color_grad(); self.sync_array(self.buffer3)
-                self.surface(); self.sync_vel()
+                self._run(self.color_grad, "array", self.buffer3)
+                self._run(self.surface, "vel")
             self.density()
         self.pressure()
         self.sync_array(self.fluid.density); self.sync_array(self.fluid.pressure)
@@ -288,34 +300,34 @@ class SphkOps:
         n, rho0 = self.n_total(), self.p.rho0
         fused = self.fused and self._surface_enabled()
         if fused:
-            self.fused_density_color_grad(True); self.sync_array(self.color_grad_buf)
+            self._run(lambda: self.fused_density_color_grad(True), "array", self.color_grad_buf)
         else:
             self.dfsph_density_alpha()
         total, it = 3.4e38, 0        # correctDivergenceError :331-363
-        self.dfsph_div_error(); self.sync_scalar(self.kappa)
+        self._run(self.dfsph_div_error, "scalar", self.kappa)
         while (it < 1 or total > self.div_thr * n * rho0) and it < self.max_iter:
-            self.dfsph_div_correct(); self.sync_vel()
-            self.dfsph_div_error(); self.sync_scalar(self.kappa)
+            self._run(self.dfsph_div_correct, "vel")
+            self._run(self.dfsph_div_error, "scalar", self.kappa)
             it += 1
             if self.div_thr >= 0:    # negative threshold: the test cannot depend on the sum (Q11) -> no host sync
                 total = self.reduce_sum(self.reduce_abs_sum(self.owned(self.error)))
         self.it_div = it
         self.gravity()
         if fused:
-            self.fused_viscosity_surface(); self.sync_vel()
+            self._run(self.fused_viscosity_surface, "vel", split=False)
         else:
-            self.viscosity(); self.sync_vel()
+            self._run(self.viscosity, "vel", split=False)
             if self._surface_enabled():
-                self.color_grad(); self.sync_array(self.buffer3)
-                self.surface(); self.sync_vel()
+                self._run(self.color_grad, "array", self.buffer3)
+                self._run(self.surface, "vel")
         total, it = 3.4e38, 0        # project :160-210
         self.permute(self.warm, 1)
-        self.dfsph_den_correct(self.warm); self.sync_vel()
-        self.dfsph_den_error(False); self.sync_scalar(self.kappa)
+        self._run(lambda: self.dfsph_den_correct(self.warm), "vel")
+        self._run(lambda: self.dfsph_den_error(False), "scalar", self.kappa)
         self.copy(self.warm, self.kappa)
         while (it < 2 or total > self.den_thr * n * rho0) and it < self.max_iter:
-            self.dfsph_den_correct(); self.sync_vel()
-            self.dfsph_den_error(True); self.sync_scalar(self.kappa)
+            self._run(self.dfsph_den_correct, "vel")
+            self._run(lambda: self.dfsph_den_error(True), "scalar", self.kappa)
             it += 1
             if it >= 2 and self.den_thr >= 0:
                 total = self.reduce_sum(self.reduce_abs_sum(self.owned(self.error)))
@@ -330,13 +342,13 @@ class SphkOps:
         self.set_use_list(self.use_list, 150 if self.use_list else 0)   # skin list: positions move inside the step
         self.permute(self.pos_last, 3)
         for _ in range(self.max_iter):
-            self.pbd_density_lambda(); self.sync_scalar(self.lam)
+            self._run(self.pbd_density_lambda, "scalar", self.lam)
             self.pbd_delta_pos_apply(); self.sync_positions()
         self.pbd_velocity_from_positions()
-        self.pbd_xsph(); self.sync_vel()
+        self._run(self.pbd_xsph, "vel", split=False)
         if self._surface_enabled():
-            self.color_grad(); self.sync_array(self.buffer3)
-            self.surface(); self.sync_vel()
+            self._run(self.color_grad, "array", self.buffer3)
+            self._run(self.surface, "vel")
         self.gravity()
         self.copy(self.pos_last, self.fluid.pos)
         self.advect()

@@ -253,6 +253,7 @@ class SlabSystem(SphkOps):
                                  C.c_void_p(self.stream.cuda_stream)), "sphk_create")
         self._alloc_solver_buffers(cap)
         self.use_list = True
+        self.overlap = os.environ.get("SPHK_SLAB_OVERLAP", "1") != "0"   # interior-first sweeps hide the halo exchange
         self._scene = None
         self._G = (C.c_float * 3)(*[float(x) for x in p.gravity])
         self._space = (C.c_float * 3)(*[float(x) for x in p.space])
@@ -355,6 +356,44 @@ class SlabSystem(SphkOps):
         for b, e in (self.ghost_l, self.ghost_r):
             if e > b:
                 check(self.L.sphk_push_range(self.ctx, self._s(), C.c_int(what), _ptr(arr), C.c_int(b), C.c_int(e - b)))
+
+    # ---- overlapped sweep + halo: boundary planes first, exchange while the interior is being computed -----------
+    def _set_active(self, b, e):
+        check(self.L.sphk_set_active_range(self.ctx, C.c_int(b), C.c_int(max(e - b, 0))))
+
+    def _run(self, op, sync=None, tensor=None, split=True):
+        if sync is None or not split or not self.overlap or self.ex.stage:
+            return super()._run(op, sync, tensor)
+        (f0, f1), (l0, l1) = self.first_plane, self.last_plane
+        own0, own1 = self.n_gl, self.n_gl + self.n_own
+        if l0 < f1:                                   # one- or two-plane slab: no interior to overlap with
+            return super()._run(op, sync, tensor)
+        self._set_active(f0, f1); op()
+        self._set_active(l0, l1); op()
+        t = self.fluid.vel if sync == "vel" else tensor
+        works = self._sync_start(t)
+        self._set_active(f1, l0); op()                # interior: no ghost neighbours, runs while the halo is in flight
+        for w in works:
+            w.wait()
+        if sync == "vel":
+            self._push(1, None)
+        elif sync == "scalar":
+            self._push(2, tensor)
+        self._set_active(own0, own1)
+
+    def _sync_start(self, t):
+        ex = self.ex
+        ops = []
+        fl = t[self.first_plane[0]:self.first_plane[1]]
+        ll = t[self.last_plane[0]:self.last_plane[1]]
+        gl, gr = t[self.ghost_l[0]:self.ghost_l[1]], t[self.ghost_r[0]:self.ghost_r[1]]
+        if ex.left is not None:
+            if fl.numel(): ops.append(dist.P2POp(dist.isend, fl, ex.left, ex.group)); ex.bytes_sent += fl.numel() * 4; ex.messages += 1
+            if gl.numel(): ops.append(dist.P2POp(dist.irecv, gl, ex.left, ex.group))
+        if ex.right is not None:
+            if ll.numel(): ops.append(dist.P2POp(dist.isend, ll, ex.right, ex.group)); ex.bytes_sent += ll.numel() * 4; ex.messages += 1
+            if gr.numel(): ops.append(dist.P2POp(dist.irecv, gr, ex.right, ex.group))
+        return dist.batch_isend_irecv(ops) if ops else []
 
     def sync_vel(self):
         self._sync(self.fluid.vel)
