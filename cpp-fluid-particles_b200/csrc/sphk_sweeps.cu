@@ -933,12 +933,25 @@ extern "C" int sphk_pbd_xsph(sphk_ctx* c, const sphk_scene* s, float xc, float r
 }
 
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_push_range(Rec* __restrict__ rec, const float* __restrict__ vel, const float* __restrict__ scalar, int begin, int count) {
+k_push_range(Rec* __restrict__ rec, const float* __restrict__ vel, const float* __restrict__ scalar,
+             const float* __restrict__ pos, const float4* __restrict__ posBuild, unsigned int* __restrict__ dispMax,
+             int begin, int count) {
     const int t = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (t >= count) return;
-    const int i = begin + t;
-    if (vel) rec_set_vel(rec + i, load3(vel, i));
-    if (scalar) rec[i].s = scalar[i];
+    float d2 = 0.f;
+    if (t < count) {
+        const int i = begin + t;
+        if (vel) rec_set_vel(rec + i, load3(vel, i));
+        if (scalar) rec[i].s = scalar[i];
+        if (pos) {
+            const float3 p = load3(pos, i);
+            rec_set_pos(rec + i, p);
+            if (posBuild) { const float3 m = p - xyz(posBuild[i]); d2 = dot3(m, m); }
+        }
+    }
+    if (pos && posBuild) {      // ghosts moved by their owner count against the skin like local moves do
+        for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+        if ((threadIdx.x & 31) == 0 && __float_as_uint(d2) > *dispMax) atomicMax(dispMax, __float_as_uint(d2));
+    }
 }
 
 extern "C" int sphk_set_active_range(sphk_ctx* c, int begin, int count) {
@@ -950,12 +963,15 @@ extern "C" int sphk_set_active_range(sphk_ctx* c, int begin, int count) {
 
 extern "C" int sphk_push_range(sphk_ctx* c, const sphk_scene* s, int what, const float* array, int begin, int count) {
     SPHK_CHECK_SCENE(c, s);
-    if (begin < 0 || count < 0 || begin + count > c->nF || what < 1 || what > 3) return SPHK_ERR_INVALID;
+    if (begin < 0 || count < 0 || begin + count > c->nF || what < 1 || what > 7) return SPHK_ERR_INVALID;
     if ((what & 2) && !array) return SPHK_ERR_INVALID;
     if (count == 0) return SPHK_OK;
+    const bool track = (what & 4) && c->listHasSkin && c->listEpoch == c->searchEpoch;
     k_push_range<<<sphk_blocks(count), SPHK_BLOCK, 0, c->stream>>>(c->rec, (what & 1) ? s->fluid.vel : nullptr,
-                                                                  (what & 2) ? array : nullptr, begin, count);
+                                                                  (what & 2) ? array : nullptr, (what & 4) ? s->fluid.pos : nullptr,
+                                                                  track ? c->snapA : nullptr, c->dispMax, begin, count);
     c->launches++;
+    if (what & 4) c->posDirty = true;
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;
 }

@@ -204,8 +204,9 @@ int sphk_export_dots(sphk_ctx* ctx, const sphk_particles* p, float* dot_xyz, flo
  * arrays (contiguous slices, sent with NCCL by the host) followed by sphk_push_range. */
 /* restrict every subsequent sweep to particles [begin, begin+count) of the fluid set (count<0: all) */
 int sphk_set_active_range(sphk_ctx* ctx, int begin, int count);
-/* copy API data of particles [begin, begin+count) into the packed records: what = 1: vel (scene->fluid.vel),
- * 2: neighbour scalar from `array` (float[n]); 3: vel and scalar */
+/* copy API data of particles [begin, begin+count) into the packed records: what is a bit mask -- 1: vel
+ * (scene->fluid.vel), 2: neighbour scalar from `array` (float[n]), 4: pos (scene->fluid.pos; PBD ghosts moved by
+ * their owner: counted against the neighbour-list skin like local moves) */
 int sphk_push_range(sphk_ctx* ctx, const sphk_scene* s, int what, const float* array, int begin, int count);
 
 /* ---- introspection for parity tests --------------------------------------------------------- */

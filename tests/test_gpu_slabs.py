@@ -22,7 +22,7 @@ def _run(nproc, extra, timeout=600):
     return json.loads(line[-1][len("SLAB_CHECK "):])
 
 
-@pytest.mark.parametrize("solver", ["dfsph", "wcsph"])
+@pytest.mark.parametrize("solver", ["dfsph", "wcsph", "pbd"])
 @pytest.mark.parametrize("world", [2, 3])
 def test_slabs_match_single_gpu_shared_device(built, solver, world):
     import torch

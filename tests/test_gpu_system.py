@@ -70,6 +70,21 @@ def test_class_layer_vs_reference_cuda(pkg, built, solver, name, jitter):
     ours_app.close(); ref_app.close()
 
 
+def test_class_layer_vs_reference_cuda_200k(pkg, built):
+    """A denser check at 216 000 fluid + 58 808 boundary particles (DFSPH 4+4): two steps against the reference's
+    own kernels."""
+    _gpu()
+    if not os.path.exists(LIBREF):
+        pytest.skip("oracle/_ref/libsphref.so not built")
+    from cpp_fluid_particles_b200 import capi
+    sc = pkg.scene.benchmark_scene("200k", "dfsph")
+    a, b = capi.SphApp(sc), capi.SphApp(sc, LIBREF)
+    for k in range(3):
+        _compare_states(a.download(), b.download(), f"200k dfsph step {k}")
+        a.step(); b.step()
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("solver", SOLVERS)
 def test_sorted_order_bit_exact_through_steps(pkg, built, solver):
     """The stable-sort permutation and cellStart stay identical to the reference while the fluid moves:
