@@ -294,7 +294,7 @@ def run_ours_single(args, pkg) -> dict:
             "alg_bytes_per_launch": n * dens["alg_bytes_per_particle"], "ms_per_launch": dens["ms"], "kernels": kernels,
             "note": "neighbour sweeps are bound by FP32 issue / L1 gather rate, not HBM (SURVEY 8d): see DESIGN.md"}
     if stats:
-        roof["list_entries_per_particle"] = stats["total"] / n      # + up to 7 group mates exchanged by warp shuffles
+        roof["neighbors_per_particle"] = stats["total"] / n
     s.close()
     del s
     torch.cuda.empty_cache()

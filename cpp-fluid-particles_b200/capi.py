@@ -32,7 +32,7 @@ SPH_APP_FUNCTIONS = [
     "sph_app_download_fluid", "sph_app_download_boundary", "sph_app_upload_fluid", "sph_app_engine",
 ]
 
-OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_GROUP_SHUFFLE, OPT_LIST_SKIN, OPT_SIMPLE_LIST_BUILD = 1, 2, 4, 5, 6
+OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_LANES_PER_PARTICLE, OPT_LIST_SKIN, OPT_SIMPLE_LIST_BUILD = 1, 2, 4, 5, 6
 
 
 class SphkGrid(C.Structure):

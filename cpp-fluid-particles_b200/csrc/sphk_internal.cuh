@@ -62,7 +62,7 @@ struct sphk_ctx {
     float skin = 0.f;                // neighbour-list skin as a fraction of R (PBD: positions move inside a step)
     bool listHasSkin = false;        // the current list was built with a skin and displacement is being tracked
     unsigned int* dispMax = nullptr; // device: max squared displacement since the list build (float bits)
-    bool groupShuffle = true;        // list sweeps: group mates (i ^ 1..7) come from partner lanes by warp shuffle, not from the list
+    int lanesPerParticle = 1;        // list sweeps: 1 = thread per particle (default, faster on B200: profiles/), 4 = warp-cooperative quad
     unsigned long long searchEpoch = 0, listEpoch = ~0ull;
     int listBegin = 0, listEnd = 0;  // particle range the current list covers
     bool posDirty = false;           // positions changed since the last search
@@ -84,7 +84,6 @@ struct DevScene {
     float4* posBuild;                // positions at list build (skin lists)
     int nF, bOff, nbrStride, kmax;
     int iBegin, iEnd;                // sweeps compute particles [iBegin, iEnd)
-    int groupShuffle;                // 1: the list excludes each particle's aligned group of 8 (handled by shuffles)
     int3 cs, org;
     float cellLength;
     float r2list;                    // candidate cut-off of the cell walk: r2cut, or (R + skin)^2 when building a skin list

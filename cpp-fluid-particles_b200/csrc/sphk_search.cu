@@ -235,7 +235,9 @@ extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
         if (value < 0 || value > 1000) return SPHK_ERR_INVALID;
         if (value * 0.001f != c->skin) { c->skin = value * 0.001f; c->listEpoch = ~0ull; }
         return SPHK_OK;
-    case SPHK_OPT_GROUP_SHUFFLE: c->groupShuffle = value != 0; c->listEpoch = ~0ull; return SPHK_OK;
+    case SPHK_OPT_LANES_PER_PARTICLE:
+        if (value != 1 && value != 4) return SPHK_ERR_INVALID;
+        c->lanesPerParticle = value; return SPHK_OK;
     default: return SPHK_ERR_INVALID;
     }
 }

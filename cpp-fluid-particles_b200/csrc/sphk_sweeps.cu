@@ -323,8 +323,7 @@ __device__ __forceinline__ float uniform_mass(const DevScene& s) {
 // boundary terms in the sum, ~1e-7 relative).  The centre cell is recomputed from the LIVE position while the
 // ranges stay those of the last search -- the reference's PBD semantics (Q7).
 template <class Op>
-__device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float4 pi, float m0,
-                                           bool skipGroup = false) {
+__device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float4 pi, float m0) {
     const int cx = cell_coord(pi.x, s.cellLength) - s.org.x, cy = cell_coord(pi.y, s.cellLength) - s.org.y,
               cz = cell_coord(pi.z, s.cellLength) - s.org.z;
     const float3 xi = xyz(pi);
@@ -343,7 +342,6 @@ __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, type
                 fetch<Op>(s, j, lo, hi);
                 const float3 d = xi - xyz(lo);
                 const float r2 = dot3(d, d);
-                if (skipGroup && (j >> 3) == (i >> 3)) continue;     // handled by the shuffle phase of k_sweep_list
                 if (r2 <= s.r2list) op.pair(acc, i, j, false, d, r2, mass_of<Op>(s, j, false, hi, m0), lo, hi, s);
             }
         }
@@ -382,48 +380,17 @@ __device__ __forceinline__ void list_pair(const DevScene& s, const Op& op, typen
     op.pair(acc, i, j, isB, d, dot3(d, d), mass_of<Op>(s, j, isB, hi, m0), lo, hi, s);
 }
 
-// List sweep.  Two phases per particle i (one thread per particle, lanes = 32 consecutive particles):
-//  S. "group" phase: the 7 other particles of i's aligned group of 8 (i ^ 1 .. i ^ 7) are cell mates or
-//     next-cell particles, i.e. very likely neighbours -- and their records are ALREADY in registers of the
-//     partner lanes (every lane loads its own record).  They are exchanged with warp shuffles and tested
-//     directly; the list builder leaves them out of the list.  This removes ~7 of ~31 gathers per particle
-//     from the L1 data pipe, the unit that bounds these sweeps (profiles/), at the price of issue slots the
-//     sweeps have to spare.
-//  L. list phase: the remaining neighbours, four at a time: one coalesced streaming int4 of indices
-//     (prefetched one batch ahead), four independent record gathers, then the math.
-// Sums are formed group-first, then in list (= reference) order.
 template <class Op>
 __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, const Op op) {
-    const int i = (s.groupShuffle ? (s.iBegin & ~31) : s.iBegin) + blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    const bool active = i >= s.iBegin && i < s.iEnd;
-    if (!s.groupShuffle && !active) return;
-    float4 lo = make_float4(1e30f, 1e30f, 1e30f, 0.f), hi = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < s.nF) rec_full(s.rec + i, lo, hi);
+    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= s.iEnd) return;
+    float4 lo, hi;
+    rec_full(s.rec + i, lo, hi);
     const float3 xi = xyz(lo);
     typename Op::Acc acc;
-    if (active) op.begin(acc, i, lo, hi, s);
-    const float m0 = uniform_mass(s);
-    if (s.groupShuffle) {
-#pragma unroll
-        for (int dlt = 1; dlt < 8; ++dlt) {
-            float4 pl, ph = make_float4(0.f, 0.f, 0.f, 0.f);
-            pl.x = __shfl_xor_sync(0xffffffffu, lo.x, dlt); pl.y = __shfl_xor_sync(0xffffffffu, lo.y, dlt);
-            pl.z = __shfl_xor_sync(0xffffffffu, lo.z, dlt); pl.w = __shfl_xor_sync(0xffffffffu, lo.w, dlt);
-            if (Op::kHi) {
-                ph.x = __shfl_xor_sync(0xffffffffu, hi.x, dlt); ph.y = __shfl_xor_sync(0xffffffffu, hi.y, dlt);
-                ph.z = __shfl_xor_sync(0xffffffffu, hi.z, dlt);
-            }
-            ph.w = __shfl_xor_sync(0xffffffffu, hi.w, dlt);
-            const int j = i ^ dlt;
-            if (active && j < s.nF) {
-                const float3 d = xi - xyz(pl);
-                const float r2 = dot3(d, d);
-                if (r2 <= s.k.r2cut) op.pair(acc, i, j, false, d, r2, ph.w, pl, ph, s);
-            }
-        }
-    }
-    if (!active) return;
+    op.begin(acc, i, lo, hi, s);
     int n = s.cnt[i];
+    const float m0 = uniform_mass(s);
     if (s.dispMax && *s.dispMax > s.dispLimit) n = s.kmax + 1;     // skin exhausted: everybody walks the cells
     if (n <= s.kmax) {
         const int nb4 = (n + 3) >> 2;
@@ -442,9 +409,52 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, con
             list_pair(s, op, acc, i, xi, j4.w, l3, h3, m0);
         }
     } else {
-        walk_cells(s, op, acc, i, lo, m0, s.groupShuffle != 0);  // more neighbours than the list keeps: exact fallback
+        walk_cells(s, op, acc, i, lo, m0);  // more neighbours than the list keeps: exact fallback
     }
     op.end(acc, i, lo, hi, s);
+}
+
+// Warp-cooperative list walk: FOUR lanes per particle, lane q takes list entries 4b+q, partial sums are combined
+// with two warp shuffles at the end.  A warp therefore covers 8 consecutive particles (one cell, or two):
+//   - the four indices of a batch of one particle are one int4, the 8 particles' int4s are 128 contiguous
+//     bytes: ONE fully coalesced line per warp request (was four);
+//   - at every step the 32 gathered records are neighbours of the SAME cell at the SAME list position, i.e. a
+//     few adjacent cache lines, instead of neighbours of four different cells (~13 lines): the L1 data pipe
+//     processes one line per wavefront, and its wavefront rate is what bounds these sweeps (ncu, profiles/).
+// The sums are formed as four interleaved partial sums (not the reference's sequential order): ~3e-7 relative.
+template <class Op>
+__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list4(const DevScene s, const Op op) {
+    const int t = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    const int q = t & 3;
+    int i = s.iBegin + (t >> 2);
+    const bool valid = i < s.iEnd;
+    if (!valid) i = s.iEnd - 1;                 // keep the quad convergent for the shuffles below
+    float4 lo, hi;
+    rec_full(s.rec + i, lo, hi);
+    const float3 xi = xyz(lo);
+    typename Op::Acc acc;
+    op.begin(acc, i, lo, hi, s);
+    int n = s.cnt[i];
+    const float m0 = uniform_mass(s);
+    if (s.dispMax && *s.dispMax > s.dispLimit) n = s.kmax + 1;
+    if (n <= s.kmax) {
+        const int nb4 = (n + 3) >> 2;
+        const size_t step = static_cast<size_t>(s.nbrStride) * 4;
+        const int* __restrict__ row = s.nbr + static_cast<size_t>(i) * 4 + q;
+        int jn = (nb4 > 0) ? __ldcs(row) : i;
+        for (int b = 0; b < nb4; ++b) {
+            const int j = jn;
+            row += step;
+            if (b + 1 < nb4) jn = __ldcs(row);
+            float4 l, h;
+            fetch<Op>(s, j, l, h);
+            list_pair(s, op, acc, i, xi, j, l, h, m0);
+        }
+    } else if (q == 0) {
+        walk_cells(s, op, acc, i, lo, m0);      // more neighbours than the list keeps: exact fallback on one lane
+    }
+    acc.sums([](float& v) { v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); });
+    if (valid && q == 0) op.end(acc, i, lo, hi, s);
 }
 
 // Dedicated neighbour-list builder (the generic k_sweep_cells<OpBuildList> is kept as the simple reference of
@@ -466,14 +476,8 @@ __device__ __forceinline__ void build_range(const DevScene& s, float3 xi, int i,
             const float3 d = xi - xyz(rec_lo(base + k));
             mask |= (dot3(d, d) <= s.r2list ? 1u : 0u) << k;
         }
-        if (off == 0) {                                // drop i itself and -- group shuffle on -- its aligned group of 8
-            const int first = (s.groupShuffle ? (i & ~7) : i) - j0, count = s.groupShuffle ? 8 : 1;
-            if (first < 32 && first + count > 0) {
-                unsigned int drop = (count == 8 ? 0xffu : 1u);
-                drop = first >= 0 ? drop << first : drop >> (-first);
-                mask &= ~drop;
-            }
-        }
+        const int self = i - (off + j0);
+        if (self >= 0 && self < 32) mask &= ~(1u << self);
         while (mask) {
             const int k = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -673,7 +677,6 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
     d.iEnd = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
     d.k = kernel_constants(s->radius);
     d.r2list = d.k.r2cut;
-    d.groupShuffle = c->groupShuffle ? 1 : 0;
     d.dispMax = nullptr; d.dispLimit = 0u; d.posBuild = nullptr;
     return d;
 }
@@ -721,8 +724,8 @@ template <class Op> static int run_sweep(sphk_ctx* c, const sphk_scene* s, const
             d.dispMax = c->dispMax;
             memcpy(&d.dispLimit, &lim, sizeof(float));
         }
-        const int first = d.groupShuffle ? (d.iBegin & ~31) : d.iBegin;
-        k_sweep_list<Op><<<sphk_blocks(d.iEnd - first), SPHK_BLOCK, 0, c->stream>>>(d, op);
+        if (c->lanesPerParticle == 4) k_sweep_list4<Op><<<sphk_blocks(4 * (d.iEnd - d.iBegin)), SPHK_BLOCK, 0, c->stream>>>(d, op);
+        else k_sweep_list<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     } else {
         k_sweep_cells<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     }

@@ -83,10 +83,11 @@ enum {
     SPHK_OPT_LIST_SKIN = 5,      /* neighbour-list skin in 1/1000 of the radius (default 0).  With a skin the list
                                     stays valid while sphk_pbd_delta_pos_apply moves particles by less than skin/2
                                     (tracked on the device; beyond that every sweep falls back to the cell walk) */
-    SPHK_OPT_GROUP_SHUFFLE = 4   /* 1 (default): in the list sweeps the 7 other particles of a particle's aligned group of
-                                    8 are exchanged between lanes with warp shuffles and left out of the list (fewer
-                                    gathers through the L1 data pipe); 0: every neighbour comes from the list and sums
-                                    are formed in the reference's order */
+    SPHK_OPT_LANES_PER_PARTICLE = 4  /* list sweeps: 1 (default) = thread per particle, sums in the reference's
+                                    sequential order; 4 = four lanes share a particle and split its neighbours,
+                                    partial sums combined by warp shuffles (measured slower on B200: the sweeps
+                                    are bound by L1 sectors per gather, which lane cooperation does not reduce;
+                                    DESIGN.md) */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

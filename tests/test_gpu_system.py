@@ -143,8 +143,8 @@ def test_python_mirror_equals_class_layer(pkg, built, solver, use_list):
             assert np.array_equal(bits(a["pos"]), bits(b["pos"])), f"{solver} step {k}"
             assert np.array_equal(bits(a["density"]), bits(b["density"]))
         else:       # same pairs, same order, but another kernel instantiation (FMA contraction may differ)
-            assert_close(b["pos"], a["pos"], tol=2e-6, what=f"{solver} step {k} pos")
-            assert_close(b["density"], a["density"], tol=5e-6, what=f"{solver} step {k} density")
+            assert_close(b["pos"], a["pos"], tol=1e-6, what=f"{solver} step {k} pos")
+            assert_close(b["density"], a["density"], tol=1e-6, what=f"{solver} step {k} density")
         app.step(); s.step()
     app.close(); s.close()
 
