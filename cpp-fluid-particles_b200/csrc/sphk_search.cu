@@ -329,6 +329,19 @@ extern "C" int sphk_refresh(sphk_ctx* c, const sphk_scene* s) {
     return SPHK_OK;
 }
 
+__global__ void __launch_bounds__(SPHK_BLOCK) k_axpy(float* __restrict__ pos, const float* __restrict__ vel, int n3, float dt) {
+    const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i < n3) pos[i] = pos[i] + dt * vel[i];
+}
+
+extern "C" int sphk_particles_advect(float* pos, const float* vel, int n, float dt, void* stream) {
+    if (!pos || !vel || n < 0) return SPHK_ERR_INVALID;
+    if (n == 0) return SPHK_OK;
+    k_axpy<<<sphk_blocks(3 * n), SPHK_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(pos, vel, 3 * n, dt);
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
 extern "C" int sphk_fill(sphk_ctx* c, float* array, int n, float value) {
     if (!c || !array || n < 0) return SPHK_ERR_INVALID;
     if (n == 0) return SPHK_OK;

@@ -41,20 +41,13 @@ Particles::Particles(const std::vector<float3>& p) : pos(p.size()), vel(p.size()
 }
 
 void Particles::advect(float dt) {
-    // pos += dt * vel.  Not on the engine's hot path (BasicSPHSolver::advect uses the fused
-    // sphk_advect); kept for API parity.  Moves particles behind the engine's back -> shadows stale.
-    if (engine_ && engine_->ok()) {
-        sphk_synchronize(engine_->ctx());
-        engine_->shadowsStale = true;
-    }
-    const size_t n = size();
-    std::vector<float3> hp(n), hv(n);
-    CUDA_CALL(cudaMemcpy(hp.data(), pos.addr(), sizeof(float3) * n, cudaMemcpyDeviceToHost));
-    CUDA_CALL(cudaMemcpy(hv.data(), vel.addr(), sizeof(float3) * n, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n; ++i) {
-        hp[i].x = hp[i].x + dt * hv[i].x; hp[i].y = hp[i].y + dt * hv[i].y; hp[i].z = hp[i].z + dt * hv[i].z;
-    }
-    CUDA_CALL(cudaMemcpy(pos.addr(), hp.data(), sizeof(float3) * n, cudaMemcpyHostToDevice));
+    // pos += dt * vel.  Not on the engine's hot path (BasicSPHSolver::advect uses the fused sphk_advect); kept for
+    // API parity.  It moves particles behind the engine's back, so the packed records are re-packed before the
+    // next sweep (shadowsStale).
+    cudaStream_t st = nullptr;
+    if (engine_ && engine_->ok()) { st = engine_->stream(); engine_->shadowsStale = true; }
+    check(sphk_particles_advect(reinterpret_cast<float*>(pos.addr()), reinterpret_cast<const float*>(vel.addr()),
+                                static_cast<int>(size()), dt, st), "sphk_particles_advect");
 }
 
 // ================================================================================================

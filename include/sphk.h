@@ -123,6 +123,10 @@ int sphk_refresh(sphk_ctx* ctx, const sphk_scene* scene);
 int sphk_boundary_mass(sphk_ctx* ctx, const sphk_particles* boundary, const int* cell_start_boundary,
                        float rho_boundary, float radius);
 
+/* Particles::advect, Particles.cu:28-36: pos += dt * vel on raw arrays (no context needed: the public method of the
+ * class API; the solvers' own advection is the fused sphk_advect).  `stream` is a cudaStream_t or NULL. */
+int sphk_particles_advect(float* pos, const float* vel, int n, float dt, void* stream);
+
 /* thrust::fill, SPHSystem.cu:73 / BasicSPHSolver.cu:78 */
 int sphk_fill(sphk_ctx* ctx, float* array, int n, float value);
 

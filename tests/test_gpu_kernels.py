@@ -281,6 +281,19 @@ def test_list_overflow_falls_back_exactly(pkg, built, O):
     s.close(); s2.close()
 
 
+def test_particles_advect_raw(pkg, built):
+    """Particles::advect (Particles.cu:28-36) on raw arrays."""
+    import ctypes as C
+    torch = _torch()
+    from cpp_fluid_particles_b200 import capi
+    L = capi.sphk()
+    pos = torch.rand((1000, 3), device="cuda"); vel = torch.randn((1000, 3), device="cuda")
+    ref = (pos.cpu().numpy() + np.float32(0.01) * vel.cpu().numpy()).astype(np.float32)
+    assert L.sphk_particles_advect(C.c_void_p(pos.data_ptr()), C.c_void_p(vel.data_ptr()), 1000, C.c_float(0.01), None) == 0
+    torch.cuda.synchronize()
+    assert relerr(pos.cpu().numpy(), ref) <= 1e-6
+
+
 def test_export_dots_vs_oracle(pkg, built, O):
     """generate_dots_CUDA (vbo.cu:26-44): positions copied, colour ramp of the density, all three branches."""
     torch = _torch()
