@@ -25,7 +25,7 @@ SPHK_FUNCTIONS = [
     "sphk_dfsph_den_error", "sphk_dfsph_den_correct", "sphk_reduce_abs_sum", "sphk_copy", "sphk_pbd_density_lambda",
     "sphk_pbd_delta_pos_apply", "sphk_pbd_velocity_from_positions", "sphk_pbd_xsph", "sphk_get_permutation",
     "sphk_list_stats", "sphk_set_active_range", "sphk_push_range", "sphk_build_neighbor_list", "sphk_get_neighbor_list", "sphk_fused_density_color_grad",
-    "sphk_fused_dfsph_density_alpha_color_grad", "sphk_fused_viscosity_surface", "sphk_export_dots", "sphk_particles_advect",
+    "sphk_fused_dfsph_density_alpha_color_grad", "sphk_fused_viscosity_surface", "sphk_export_dots", "sphk_particles_advect", "sphk_add_launches",
 ]
 SPH_APP_FUNCTIONS = [
     "sph_app_create", "sph_app_destroy", "sph_app_step", "sph_app_fluid_size", "sph_app_boundary_size",

@@ -262,6 +262,7 @@ extern "C" const char* sphk_error_string(int code) {
 }
 
 extern "C" long long sphk_launch_count(const sphk_ctx* c) { return c ? c->launches : 0; }
+extern "C" int sphk_add_launches(sphk_ctx* c, long long n) { if (!c) return SPHK_ERR_INVALID; c->launches += n; return SPHK_OK; }
 
 extern "C" int sphk_device_rcp(sphk_ctx* c, float x, float* out_host) {
     if (!c || !out_host) return SPHK_ERR_INVALID;

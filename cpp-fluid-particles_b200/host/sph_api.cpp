@@ -4,6 +4,7 @@
 #include "sph_api.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <limits>
 
 using sphb200::check;
@@ -322,6 +323,7 @@ SPHSystem::SPHSystem(std::shared_ptr<SPHParticles>& fluidParticles, std::shared_
     _boundaries->bindEngine(_engine);
     CUDA_CALL(cudaEventCreate(&_evStart));
     CUDA_CALL(cudaEventCreate(&_evStop));
+    if (const char* g = std::getenv("SPHK_STEP_GRAPH")) _graphEnabled = g[0] != '0';
     if (!_engine->ok()) return;
     // SPHSystem.cu:68-76
     neighborSearch(_boundaries, cellStartBoundary);
@@ -333,6 +335,7 @@ SPHSystem::SPHSystem(std::shared_ptr<SPHParticles>& fluidParticles, std::shared_
 
 SPHSystem::~SPHSystem() noexcept {
     if (_engine && _engine->ok()) sphk_synchronize(_engine->ctx());
+    if (_graphExec) cudaGraphExecDestroy(_graphExec);
     if (_evStart) cudaEventDestroy(_evStart);
     if (_evStop) cudaEventDestroy(_evStop);
 }
@@ -352,20 +355,67 @@ void SPHSystem::neighborSearch(const std::shared_ptr<SPHParticles>& particles, D
 }
 
 // SPHSystem.cu:129-158
+bool SPHSystem::solverIsGraphSafe() const {
+    const auto* known = dynamic_cast<const BasicSPHSolver*>(_solver.get());   // unknown BaseSolver subclasses: never
+    return known && known->stepIsGraphSafe();
+}
+
+void SPHSystem::setStepGraph(bool on) {
+    _graphEnabled = on;
+    if (!on && _graphExec) { sphk_synchronize(_engine->ctx()); cudaGraphExecDestroy(_graphExec); _graphExec = nullptr; }
+}
+
+// SPHSystem.cu:129-158.  Small scenes are launch-bound (~45 kernels of a few microseconds per DFSPH step): once
+// two plain steps have run (all lazy allocations done), a fixed-iteration step is captured into a CUDA graph and
+// replayed -- same kernels, same order, same arguments (all scene parameters are const members).
 float SPHSystem::step() {
     if (!_engine->ok()) return 0.0f;
     cudaStream_t st = _engine->stream();
+    sphk_ctx* ctx = _engine->ctx();
     CUDA_CALL(cudaEventRecord(_evStart, st));
-    neighborSearch(_fluids, cellStartFluid);
-    try {
-        _solver->step(_fluids, _boundaries, cellStartFluid, cellStartBoundary, _spaceSize, _cellSize, _sphCellLength,
-                      _sphSmoothingRadius, _dt, _sphRho0, _sphRhoBoundary, _sphStiff, _sphVisc, _sphG,
-                      _sphSurfaceTensionIntensity, _sphAirPressure);
-        check(sphk_synchronize(_engine->ctx()), "step");
-    } catch (const char* s) {
-        std::cout << s << "\n";
-    } catch (...) {
-        std::cout << "Unknown Exception at " << __FILE__ << ": line " << __LINE__ << "\n";
+    if (_graphExec) {
+        CUDA_CALL(cudaGraphLaunch(_graphExec, st));
+        sphk_add_launches(ctx, _graphLaunches);
+        check(sphk_synchronize(ctx), "step");
+    } else {
+        const bool capture = _graphEnabled && _plainSteps >= 2 && solverIsGraphSafe();
+        const long long launches0 = sphk_launch_count(ctx);
+        bool captured = false;
+        if (capture) captured = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        bool ok = false;
+        try {
+            neighborSearch(_fluids, cellStartFluid);
+            _solver->step(_fluids, _boundaries, cellStartFluid, cellStartBoundary, _spaceSize, _cellSize, _sphCellLength,
+                          _sphSmoothingRadius, _dt, _sphRho0, _sphRhoBoundary, _sphStiff, _sphVisc, _sphG,
+                          _sphSurfaceTensionIntensity, _sphAirPressure);
+            ok = true;
+        } catch (const char* s) {
+            std::cout << s << "\n";
+        } catch (...) {
+            std::cout << "Unknown Exception at " << __FILE__ << ": line " << __LINE__ << "\n";
+        }
+        if (captured) {
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph && ok &&
+                cudaGraphInstantiate(&_graphExec, graph, 0) == cudaSuccess) {
+                _graphLaunches = sphk_launch_count(ctx) - launches0;
+                CUDA_CALL(cudaGraphLaunch(_graphExec, st));     // the captured step has not run yet: run it now
+            } else {
+                cudaGetLastError();
+                _graphExec = nullptr;
+                _graphEnabled = false;                          // capture refused (e.g. a library call): stay on plain launches
+                printf("SPHSystem: step graph capture failed, continuing with plain launches\n");
+                neighborSearch(_fluids, cellStartFluid);
+                try {
+                    _solver->step(_fluids, _boundaries, cellStartFluid, cellStartBoundary, _spaceSize, _cellSize,
+                                  _sphCellLength, _sphSmoothingRadius, _dt, _sphRho0, _sphRhoBoundary, _sphStiff, _sphVisc,
+                                  _sphG, _sphSurfaceTensionIntensity, _sphAirPressure);
+                } catch (...) {}
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (ok) ++_plainSteps;
+        check(sphk_synchronize(ctx), "step");
     }
     float milliseconds = 0.0f;
     CUDA_CALL(cudaEventRecord(_evStop, st));

@@ -165,6 +165,8 @@ public:
     explicit BasicSPHSolver(int num) : bufferFloat3(num), bufferColorGrad(num) {}
     // addition: false = one kernel per reference launch site (the per-op C-ABI path); true (default) = fused sweeps
     void setFusedSweeps(bool on) { fusedSweeps_ = on; }
+    // addition: true when step() enqueues the same kernel sequence every call and never synchronises the host
+    virtual bool stepIsGraphSafe() const { return true; }
     virtual ~BasicSPHSolver() noexcept {}
     virtual void step(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
                       const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
@@ -214,6 +216,7 @@ public:
                       const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
                       int3 cellSize, float cellLength, float radius, float dt, float rho0, float rhoB, float stiff,
                       float visc, float3 G, float surfaceTensionIntensity, float airPressure) override;
+    bool stepIsGraphSafe() const override { return densityErrorThreshold < 0.0f && divergenceErrorThreshold < 0.0f; }
     int lastDivergenceIterations() const { return itDiv_; }   // addition: iteration counts of the last step
     int lastDensityIterations() const { return itDen_; }
 protected:
@@ -252,6 +255,7 @@ public:
                       const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
                       int3 cellSize, float cellLength, float radius, float dt, float rho0, float rhoB, float stiff,
                       float visc, float3 G, float surfaceTensionIntensity, float airPressure) override;
+    bool stepIsGraphSafe() const override { return posLastInitialized; }
     void initializePosLast(const DArray<float3>& posFluid) {
         CUDA_CALL(cudaMemcpy(fluidPosLast.addr(), posFluid.addr(), sizeof(float3) * fluidPosLast.length(),
                              cudaMemcpyDeviceToDevice));
@@ -300,6 +304,7 @@ public:
     const DArray<int>& getCellStartFluid() const { return cellStartFluid; }
     const DArray<int>& getCellStartBoundary() const { return cellStartBoundary; }
     const std::shared_ptr<sphb200::Engine>& engine() const { return _engine; }
+    void setStepGraph(bool on);   // replay each step as one CUDA graph when the solver allows it (default on)
 
 private:
     std::shared_ptr<SPHParticles> _fluids;
@@ -321,6 +326,12 @@ private:
     const int3 _cellSize;
     std::shared_ptr<sphb200::Engine> _engine;
     cudaEvent_t _evStart = nullptr, _evStop = nullptr;
+    // CUDA graph of one whole step (fixed-iteration solvers only: the kernel sequence is then the same every step)
+    cudaGraphExec_t _graphExec = nullptr;
+    long long _graphLaunches = 0;
+    int _plainSteps = 0;
+    bool _graphEnabled = true;
+    bool solverIsGraphSafe() const;
     void computeBoundaryMass();
     void neighborSearch(const std::shared_ptr<SPHParticles>& particles, DArray<int>& cellStart);
 };

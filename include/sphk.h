@@ -98,6 +98,8 @@ int  sphk_synchronize(sphk_ctx* ctx);
 const char* sphk_error_string(int code);
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 long long sphk_launch_count(const sphk_ctx* ctx);
+/* account for kernels replayed from a captured CUDA graph (the host-side counter does not see them) */
+int  sphk_add_launches(sphk_ctx* ctx, long long n);
 /* rcp.approx(cell_length) as the device computes it (bit pattern as float): lets a CPU checker
  * reproduce the GPU cell hash bit-for-bit */
 int  sphk_device_rcp(sphk_ctx* ctx, float x, float* out_host);
