@@ -9,14 +9,16 @@ Rank g owns global cell planes [X_g, X_{g+1}).  Its libsphk context covers the l
 
         [ ghost-left (plane X_g - 1) | owned | ghost-right (plane X_{g+1}) ]
 
-Per step (`SlabSystem.begin_step`):
-  A. search the owned particles: those that left the slab during the last advect now sit in the two ghost
-     planes, i.e. at the two ends of the sorted array  -> emigrants are contiguous slices;
-  B. exchange emigrants with the x-neighbours (count, then one packed message per neighbour);
-  C. search owned' = stay + immigrants: the first / last owned planes are contiguous slices;
-  D. exchange those halo planes (count + packed message) and assemble [ghostL | owned' | ghostR];
-  E. search the assembled set (already sorted: identity permutation) -> cell ranges, packed records,
-     neighbour list;  sweeps are then restricted to the owned range (sphk_set_active_range).
+Per step (`SlabSystem.begin_step`) -- ONE exchange and ONE search:
+  1. every rank sends its two outermost owned planes per side (contiguous slices of last step's sorted order; a
+     particle moves less than one plane per step, so these are all particles that can now be in the neighbour's
+     last owned plane or in its ghost plane) -- count first, then one packed message per neighbour;
+  2. it searches [candidates-from-left | own particles | candidates-from-right] once.  The sort itself decides
+     everything: local plane 0 / w+1 = ghosts (own particles that left the slab included), planes 1..w = owned
+     (immigrants included), keys outside the local grid = candidates that belong to neither -> sorted to the end
+     and ignored (no cell range contains them).  Ownership is decided by the global cell plane on both sides, so
+     no particle is lost or duplicated;
+  3. sweeps are restricted to the owned range (sphk_set_active_range).
 During the solver step every field a sweep reads from neighbours and a previous sweep changed is refreshed
 on the ghosts: the owner's first/last plane slice of the API array is sent to the neighbour's ghost slice
 (contiguous -> no packing kernels), then sphk_push_range mirrors it into the packed records.
@@ -132,62 +134,44 @@ class SlabExchange:
         return fl, fr
 
 
-def assemble_slab(ex: SlabExchange, arrays, alt, offset: int, n_own: int, search, bounds):
-    """Steps A-D of the module docstring.
+def exchange_candidates(ex: SlabExchange, arrays, alt, own: tuple, to_left: tuple, to_right: tuple) -> int:
+    """Step 1 of the module docstring + the concatenation for step 2.
 
-    arrays   list of per-particle tensors (first dimension = particle slot, e.g. pos (cap,3), vel (cap,3),
-             history (cap,)); the owned particles occupy slots [offset, offset + n_own) in any order
-    alt      same-shaped scratch tensors (the result is assembled there, then the two sets are swapped in place)
-    search(offset, n)  sorts slots [offset, offset+n) of `arrays` by local cell key in place (stable)
-    bounds() host ints (s0, s1, s2, sw, sw1, send) RELATIVE to the searched slice: where local planes 0, 1, 2, w,
-             w+1 start and where plane w+1 ends (= number of in-grid particles); planes 0 / w+1 are the ghost
-             planes, 1..w the owned ones
-    On return arrays[:total] = [ghostL | stay | immigrants-from-left | immigrants-from-right | ghostR] (owned part
-    not yet sorted: the caller's final search sorts the whole set) and (n_ghost_left, n_owned_new, n_ghost_right)
-    is returned.
+    arrays    list of per-particle tensors (first dimension = slot); alt: same-shaped scratch set
+    own       (begin, end): slots of the particles this rank owned at the end of the last step (sorted order)
+    to_left   (begin, end) inside `own`: its first two owned planes;  to_right: its last two owned planes
+    Returns n_all; afterwards arrays[:n_all] = [candidates from the left | own particles | candidates from the right].
 
-    Ordering contract for the later field halos: the halo message of the first owned plane is
-    [stay particles of that plane (sorted), immigrants from the left]; both the sender's and the receiver's
-    final (stable) sorts see these particles in this relative order, so the sender's sorted first plane and the
-    receiver's sorted ghost plane are the same sequence (same for the last plane)."""
-    # A. classify by sorting: particles that left the slab sit in the ghost planes, i.e. at the two ends
-    search(offset, n_own)
-    s0, s1, s2, sw, sw1, send = bounds()
-    if s0 != 0 or send != n_own:
-        raise RuntimeError(f"slab rank {ex.rank}: a particle moved more than one cell plane in one step "
-                           f"({n_own - (send - s0)} of {n_own} outside the local grid); reduce dt or rebalance")
+    Ordering contract for the later field halos (why the concatenation order is fixed): inside a cell the final
+    stable sort keeps [left candidates, own, right candidates].  For the particles of a boundary plane this is the
+    same relative order on the owner and on the neighbour that holds them as ghosts -- an immigrant precedes the
+    natives on its new owner (it came in the left/right candidate block ... of the side it came from) exactly as it
+    does on its old owner (where it is an own particle and the natives are candidates from that side) -- so the
+    owner's sorted boundary plane and the neighbour's sorted ghost plane are the same sequence."""
     widths = [1 if a.dim() == 1 else a.shape[1] for a in arrays]
 
-    def pack(lo, hi):                                   # rows [lo, hi) of the searched slice -> (m, sum(widths))
-        return torch.cat([a[offset + lo:offset + hi].reshape(hi - lo, w_) for a, w_ in zip(arrays, widths)], 1).contiguous()
+    def pack(lo, hi):
+        return torch.cat([a[lo:hi].reshape(hi - lo, w_) for a, w_ in zip(arrays, widths)], 1).contiguous()
 
     def pieces(rows):
         out, c = [], 0
-        for a, w in zip(arrays, widths):
-            out.append(rows[:, c:c + w].reshape((rows.shape[0],) + tuple(a.shape[1:])))
-            c += w
+        for a, w_ in zip(arrays, widths):
+            out.append(rows[:, c:c + w_].reshape((rows.shape[0],) + tuple(a.shape[1:])))
+            c += w_
         return out
 
-    # B. migrate (few particles): emigrants-left = plane 0, emigrants-right = plane w+1
-    imm_l, imm_r = ex.exchange_rows(pack(0, s1), pack(sw1, n_own))
-    n_stay = sw1 - s1
-    n_new = n_stay + imm_l.shape[0] + imm_r.shape[0]
-    # D. halo planes from stay + immigrants (no second sort): first owned plane -> left, last -> right
-    w_is_1 = (sw == s1)                                 # a one-plane slab: first plane == last plane
-    first = [pack(s1, s2), imm_l] + ([imm_r] if w_is_1 else [])
-    last = [pack(sw, sw1)] + ([imm_l] if w_is_1 else []) + [imm_r]
-    gl, gr = ex.exchange_rows(torch.cat(first, 0), torch.cat(last, 0))
-    total = gl.shape[0] + n_new + gr.shape[0]
+    from_l, from_r = ex.exchange_rows(pack(*to_left), pack(*to_right))
+    n_own = own[1] - own[0]
+    n_all = from_l.shape[0] + n_own + from_r.shape[0]
     cap = arrays[0].shape[0]
-    if total > cap:
-        raise RuntimeError(f"slab rank {ex.rank}: capacity {cap} exceeded by {total} local particles")
-    # assemble in the scratch set: [ghostL | stay | immL | immR | ghostR]
+    if n_all > cap:
+        raise RuntimeError(f"slab rank {ex.rank}: capacity {cap} exceeded by {n_all} local particles")
     o = 0
-    for rows in (gl, None, imm_l, imm_r, gr):
+    for rows in (from_l, None, from_r):
         if rows is None:
             for a, d in zip(arrays, alt):
-                d[o:o + n_stay] = a[offset + s1:offset + sw1]
-            o += n_stay
+                d[o:o + n_own] = a[own[0]:own[1]]
+            o += n_own
         else:
             m = rows.shape[0]
             if m:
@@ -195,8 +179,19 @@ def assemble_slab(ex: SlabExchange, arrays, alt, offset: int, n_own: int, search
                     d[o:o + m] = pc
             o += m
     for a, d in zip(arrays, alt):
-        a[:total] = d[:total]
-    return gl.shape[0], n_new, gr.shape[0]
+        a[:n_all] = d[:n_all]
+    return n_all
+
+
+def plane_ranges(b: tuple, w: int):
+    """From the plane offsets (s0, s1, s2, s3, s_{w-1}, s_w, s_{w+1}, s_end) of a sorted local set: the owned range,
+    the two outermost owned planes per side (next step's candidates), first / last owned plane, ghost ranges."""
+    s0, s1, s2, s3, swm1, sw, sw1, send = b
+    own = (s1, sw1)
+    to_left = (s1, min(s3, sw1) if w >= 2 else sw1)
+    to_right = (max(swm1, s1) if w >= 2 else s1, sw1)
+    return {"own": own, "to_left": to_left, "to_right": to_right, "first": (s1, s2 if w >= 2 else sw1),
+            "last": (sw if w >= 2 else s1, sw1), "ghost_l": (s0, s1), "ghost_r": (sw1, send)}
 
 
 class SlabSystem(SphkOps):
@@ -261,6 +256,7 @@ class SlabSystem(SphkOps):
         self._G = (C.c_float * 3)(*[float(x) for x in p.gravity])
         self._space = (C.c_float * 3)(*[float(x) for x in p.space])
         self.n_own, self.n_gl, self.n_gr = mine.shape[0], 0, 0
+        self._ranges = None            # plane ranges of the last sorted local set
         # boundary: already in global sorted order -> identity permutation; masses given (not recomputed)
         # (the search's gather packs mass[s] of the sorted slot s into the records: the masses set above)
         self.search_boundary()
@@ -302,23 +298,19 @@ class SlabSystem(SphkOps):
             arrs.append(self.pos_last)
         return arrs
 
-    def _search_slice(self, offset, n):
-        """search(offset, n) for assemble_slab: the C-ABI neighbour search on slots [offset, offset+n)."""
-        f = self.fluid
-        view = ParticleSet.__new__(ParticleSet)
-        view.n = n
-        view.pos, view.vel, view.mass = f.pos[offset:], f.vel[offset:], f.mass[offset:]
-        view.density, view.pressure, view.p2c = f.density[offset:], f.pressure[offset:], f.p2c[offset:]
-        p = view.abi()
-        check(self.L.sphk_neighbor_search(self.ctx, 0, C.byref(p), _ptr(self.cs_fluid)), "sphk_neighbor_search(f)")
+    def _search_all(self, n):
+        """The C-ABI neighbour search over slots [0, n) + the same permutation for the history array."""
+        self.fluid.n = n
+        self._scene = None
+        self.search_fluid()
         if self.solver == "dfsph":
-            check(self.L.sphk_permute(self.ctx, _ptr(self.warm[offset:]), C.c_int(1), C.c_int(n)), "sphk_permute")
+            self.permute(self.warm, 1)
         elif self.solver == "pbd":
-            check(self.L.sphk_permute(self.ctx, _ptr(self.pos_last[offset:]), C.c_int(3), C.c_int(n)), "sphk_permute")
+            self.permute(self.pos_last, 3)
 
     def _bounds(self):
         pc, w = self.plane_cells, self.w
-        idx = torch.tensor([0, pc, 2 * pc, w * pc, (w + 1) * pc, (w + 2) * pc], device=self.device)
+        idx = torch.tensor([0, pc, 2 * pc, 3 * pc, max(w - 1, 0) * pc, w * pc, (w + 1) * pc, (w + 2) * pc], device=self.device)
         return tuple(self.cs_fluid[idx].cpu().tolist())
 
     def begin_step(self):
@@ -326,24 +318,29 @@ class SlabSystem(SphkOps):
         arrays = self._carried()
         if not hasattr(self, "_alt"):
             self._alt = [torch.empty_like(a) for a in arrays]
-        self.n_gl, self.n_own, self.n_gr = assemble_slab(self.ex, arrays, self._alt, self.n_gl, self.n_own,
-                                                         self._search_slice, self._bounds)
-        n = self.n_gl + self.n_own + self.n_gr
-        self.fluid.n = n
-        self._scene = None
-        self.search_fluid()                              # E: sorts [ghostL | owned' | ghostR]; ranges + records
-        if self.solver == "dfsph":
-            self.permute(self.warm, 1)
-        elif self.solver == "pbd":
-            self.permute(self.pos_last, 3)
-        check(self.L.sphk_set_active_range(self.ctx, C.c_int(self.n_gl), C.c_int(self.n_own)))
-        # owned first/last plane slices and ghost slices for the field syncs
-        _, s1, s2, sw, sw1, _ = self._bounds()
-        assert s1 == self.n_gl and sw1 == self.n_gl + self.n_own, "ghost planes do not bracket the owned range"
-        self.first_plane = (s1, s2)                      # [begin, end) in local arrays
-        self.last_plane = (sw, sw1)
-        self.ghost_l = (0, self.n_gl)
-        self.ghost_r = (self.n_gl + self.n_own, n)
+        if self._ranges is None:                         # very first step: sort the initial set once
+            self._search_all(self.n_own)
+            b = self._bounds()
+            if b[7] != self.n_own:
+                raise RuntimeError(f"slab rank {self.rank}: initial partition left particles outside the local grid")
+            r = plane_ranges(b, self.w)
+            # the host-side initial partition may be one plane off for a few particles (it does not use the device
+            # hash): treat everything local as "own" and include the ghost planes in the candidates once
+            r["own"] = (b[0], b[7])
+            r["to_left"] = (b[0], r["to_left"][1])
+            r["to_right"] = (r["to_right"][0], b[7])
+            self._ranges = r
+        r = self._ranges
+        n_all = exchange_candidates(self.ex, arrays, self._alt, r["own"], r["to_left"], r["to_right"])
+        self._search_all(n_all)
+        b = self._bounds()
+        self._ranges = r = plane_ranges(b, self.w)
+        self.n_gl = r["ghost_l"][1] - r["ghost_l"][0]
+        self.n_own = r["own"][1] - r["own"][0]
+        self.n_gr = r["ghost_r"][1] - r["ghost_r"][0]
+        check(self.L.sphk_set_active_range(self.ctx, C.c_int(r["own"][0]), C.c_int(self.n_own)))
+        self.first_plane, self.last_plane = r["first"], r["last"]
+        self.ghost_l, self.ghost_r = r["ghost_l"], r["ghost_r"]
         if self.use_list:
             self.set_use_list(True, 150 if self.solver == "pbd" else 0)
             self.build_neighbor_list()
@@ -368,7 +365,7 @@ class SlabSystem(SphkOps):
         if sync is None or not split or not self.overlap or self.ex.stage:
             return super()._run(op, sync, tensor)
         (f0, f1), (l0, l1) = self.first_plane, self.last_plane
-        own0, own1 = self.n_gl, self.n_gl + self.n_own
+        own0, own1 = self._ranges["own"]
         if l0 < f1:                                   # one- or two-plane slab: no interior to overlap with
             return super()._run(op, sync, tensor)
         self._set_active(f0, f1); op()
@@ -415,7 +412,7 @@ class SlabSystem(SphkOps):
         self._push(4, None)
 
     def owned(self, t):
-        return t[self.n_gl:self.n_gl + self.n_own]
+        return t[self._ranges["own"][0]:self._ranges["own"][1]]
 
     def n_total(self) -> int:
         if not hasattr(self, "_n_total"):
@@ -442,7 +439,7 @@ class SlabSystem(SphkOps):
     def owned_state(self) -> dict:
         """Owned particles of this rank (host arrays)."""
         self.synchronize()
-        a, b = self.n_gl, self.n_gl + self.n_own
+        a, b = self._ranges["own"]
         g = lambda t: t[a:b].detach().cpu().numpy()  # noqa: E731
         return {"pos": g(self.fluid.pos), "vel": g(self.fluid.vel), "density": g(self.fluid.density)}
 

@@ -35,12 +35,17 @@ def _worker(rank, world, port, steps, q):
     x0, x1 = cuts[rank], cuts[rank + 1]
     w = x1 - x0
     ex = slabs.SlabExchange(rank, world, "cpu")
-    mine = (plane >= x0) & (plane < x1)
+    # deliberately sloppy initial partition (like the host-side approximation of the device hash): shift the cut
+    # by up to one plane for some particles
+    fuzzy = plane + (rng.integers(0, 20, n) == 0) * rng.integers(-1, 2, n)
+    fuzzy = np.clip(fuzzy, 0, CX - 1)
+    fuzzy = np.where(np.abs(fuzzy - plane) <= 1, fuzzy, plane)
+    mine = (fuzzy >= x0) & (fuzzy < x1)
     cap = n
     P, V, ID = torch.zeros((cap, 3)), torch.zeros((cap, 3)), torch.zeros(cap)
     alt = [torch.zeros((cap, 3)), torch.zeros((cap, 3)), torch.zeros(cap)]
-    n_own, gl = int(mine.sum()), 0
-    P[:n_own] = torch.from_numpy(pos[mine]); ID[:n_own] = torch.from_numpy(ids[mine])
+    n_local = int(mine.sum())
+    P[:n_local] = torch.from_numpy(pos[mine]); ID[:n_local] = torch.from_numpy(ids[mine])
     state = {}
 
     def keys_of(p):
@@ -50,47 +55,54 @@ def _worker(rank, world, port, steps, q):
         k = (lx * CY + c[:, 1]) * CZ + c[:, 2]
         return np.where(ok, k, (w + 2) * CY * CZ)
 
-    def search(off, m):                                   # stand-in for sphk_neighbor_search: stable sort by key
-        k = keys_of(P[off:off + m])
+    def search(m):                                        # stand-in for sphk_neighbor_search: stable sort by key
+        k = keys_of(P[:m])
         o = torch.from_numpy(np.argsort(k, kind="stable"))
         for a in (P, V, ID):
-            a[off:off + m] = a[off:off + m][o]
+            a[:m] = a[:m][o]
         state["keys"] = k[o.numpy()]
 
     def bounds():
         pc = CY * CZ
-        return tuple(int(np.searchsorted(state["keys"], c * pc, side="left")) for c in (0, 1, 2, w, w + 1, w + 2))
+        return tuple(int(np.searchsorted(state["keys"], c * pc, side="left")) for c in (0, 1, 2, 3, max(w - 1, 0), w, w + 1, w + 2))
 
-    ok = True
+    # first step as in SlabSystem.begin_step: everything local is "own", ghost planes included in the candidates
+    search(n_local)
+    b0 = bounds()
+    r = slabs.plane_ranges(b0, w)
+    r["own"] = (b0[0], b0[7]); r["to_left"] = (b0[0], r["to_left"][1]); r["to_right"] = (r["to_right"][0], b0[7])
+    ok = b0[7] == n_local
     for step in range(steps):
-        # every rank moves the GLOBAL set identically (|dx| < 1 plane), and its own particles accordingly
-        dx = rng.uniform(-0.45, 0.45, (n, 3)).astype(np.float32)
-        dx[:, 1:] *= 0.2
-        newpos = pos + dx
-        newpos[:, 0] = np.clip(newpos[:, 0], 0.05, CX - 0.05)
-        newpos[:, 1] = np.clip(newpos[:, 1], 0.01, CY - 0.01); newpos[:, 2] = np.clip(newpos[:, 2], 0.01, CZ - 0.01)
-        pos = newpos
-        my_ids = ID[gl:gl + n_own].numpy().astype(np.int64)
-        P[gl:gl + n_own] = torch.from_numpy(pos[my_ids])
-        gl, n_own, gr = slabs.assemble_slab(ex, [P, V, ID], alt, gl, n_own, search, bounds)
-        total = gl + n_own + gr
-        search(0, total)                                  # step E: the final sort of the assembled set
-        k = keys_of(P[:total])
-        ok &= bool(np.all(np.diff(k) >= 0))
-        loc_ids = ID[:total].numpy().astype(np.int64)
+        if step > 0:
+            # every rank moves the GLOBAL set identically (|dx| < 1 plane), and its own particles accordingly
+            dx = rng.uniform(-0.45, 0.45, (n, 3)).astype(np.float32)
+            dx[:, 1:] *= 0.2
+            newpos = pos + dx
+            newpos[:, 0] = np.clip(newpos[:, 0], 0.05, CX - 0.05)
+            newpos[:, 1] = np.clip(newpos[:, 1], 0.01, CY - 0.01); newpos[:, 2] = np.clip(newpos[:, 2], 0.01, CZ - 0.01)
+            pos = newpos
+            a0, a1 = r["own"]
+            my_ids = ID[a0:a1].numpy().astype(np.int64)
+            P[a0:a1] = torch.from_numpy(pos[my_ids])          # "advect": same slots, new positions
+        n_all = slabs.exchange_candidates(ex, [P, V, ID], alt, r["own"], r["to_left"], r["to_right"])
+        search(n_all)
+        r = slabs.plane_ranges(bounds(), w)
+        (o0, o1), (g0, g1), (h0, h1) = r["own"], r["ghost_l"], r["ghost_r"]
+        k = keys_of(P[:h1])
+        ok &= bool(np.all(np.diff(k) >= 0)) and g0 == 0 and g1 == o0 and o1 == h0
+        loc_ids = ID[:h1].numpy().astype(np.int64)
         gplane = np.floor(pos[:, 0]).astype(np.int64)
-        ok &= set(loc_ids[gl:gl + n_own].tolist()) == set(np.nonzero((gplane >= x0) & (gplane < x1))[0].tolist())
-        ok &= set(loc_ids[:gl].tolist()) == set(np.nonzero(gplane == x0 - 1)[0].tolist())
-        ok &= set(loc_ids[gl + n_own:total].tolist()) == set(np.nonzero(gplane == x1)[0].tolist())
-        ok &= bool(np.array_equal(P[:total].numpy(), pos[loc_ids]))
+        ok &= set(loc_ids[o0:o1].tolist()) == set(np.nonzero((gplane >= x0) & (gplane < x1))[0].tolist())
+        ok &= len(set(loc_ids[o0:o1].tolist())) == o1 - o0            # no duplicates
+        ok &= set(loc_ids[g0:g1].tolist()) == set(np.nonzero(gplane == x0 - 1)[0].tolist())
+        ok &= set(loc_ids[h0:h1].tolist()) == set(np.nonzero(gplane == x1)[0].tolist())
+        ok &= bool(np.array_equal(P[:h1].numpy(), pos[loc_ids]))
         # field halo: owners publish f = 2*id + step; ghosts must receive exactly that, in the ghost's SORTED order
-        # (this is the ordering contract of assemble_slab's docstring)
+        # (the ordering contract of exchange_candidates' docstring)
         f = torch.zeros(cap)
-        f[gl:gl + n_own] = 2 * ID[gl:gl + n_own] + step
-        s0, s1, s2, sw, sw1, send = bounds()
-        ok &= (s1 == gl) and (sw1 == gl + n_own)
-        ex.exchange(f[s1:s2].contiguous(), f[sw:sw1].contiguous(), f[0:gl], f[gl + n_own:total])
-        ok &= bool(torch.equal(f[:total], 2 * ID[:total] + step))
+        f[o0:o1] = 2 * ID[o0:o1] + step
+        ex.exchange(f[r["first"][0]:r["first"][1]].contiguous(), f[r["last"][0]:r["last"][1]].contiguous(), f[g0:g1], f[h0:h1])
+        ok &= bool(torch.equal(f[:h1], 2 * ID[:h1] + step))
     allok = [None] * world
     dist.all_gather_object(allok, bool(ok))
     if rank == 0:
