@@ -299,14 +299,12 @@ class SlabSystem(SphkOps):
         return arrs
 
     def _search_all(self, n):
-        """The C-ABI neighbour search over slots [0, n) + the same permutation for the history array."""
+        """The C-ABI neighbour search over slots [0, n).  The history array (DFSPH warm stiffness, PBD last positions)
+        is NOT permuted here: the solver sequence does that itself with the same permutation (DFSPHSolver.cu:170-171,
+        PBDSolver.cu:84-85), exactly as on one GPU."""
         self.fluid.n = n
         self._scene = None
         self.search_fluid()
-        if self.solver == "dfsph":
-            self.permute(self.warm, 1)
-        elif self.solver == "pbd":
-            self.permute(self.pos_last, 3)
 
     def _bounds(self):
         pc, w = self.plane_cells, self.w
@@ -319,7 +317,7 @@ class SlabSystem(SphkOps):
         if not hasattr(self, "_alt"):
             self._alt = [torch.empty_like(a) for a in arrays]
         if self._ranges is None:                         # very first step: sort the initial set once
-            self._search_all(self.n_own)
+            self._search_all(self.n_own)                 # (history arrays are still all-zero: nothing to permute)
             b = self._bounds()
             if b[7] != self.n_own:
                 raise RuntimeError(f"slab rank {self.rank}: initial partition left particles outside the local grid")
@@ -341,6 +339,9 @@ class SlabSystem(SphkOps):
         check(self.L.sphk_set_active_range(self.ctx, C.c_int(r["own"][0]), C.c_int(self.n_own)))
         self.first_plane, self.last_plane = r["first"], r["last"]
         self.ghost_l, self.ghost_r = r["ghost_l"], r["ghost_r"]
+        if os.environ.get("SPHK_SLAB_DEBUG"):
+            print(f"[slab {self.rank}] bounds {b} first {self.first_plane} last {self.last_plane} ghosts {self.ghost_l} {self.ghost_r} "
+                  f"to_left {r['to_left']} to_right {r['to_right']} n_all {n_all}", flush=True)
         if self.use_list:
             self.set_use_list(True, 150 if self.solver == "pbd" else 0)
             self.build_neighbor_list()

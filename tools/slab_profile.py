@@ -26,7 +26,7 @@ def wrap(obj, name, label):
         e0, e1 = ev(), ev(); e0.record(); t0 = _t.perf_counter(); r = inner(*a, **k); dt = _t.perf_counter() - t0; e1.record()
         marks.setdefault(label, []).append((e0, e1, dt)); return r
     setattr(obj, name, f)
-wrap(s, "_search_slice", "searchA"); wrap(s, "search_fluid", "searchE"); wrap(s, "build_neighbor_list", "build")
+wrap(s, "search_fluid", "search"); wrap(s, "build_neighbor_list", "build")
 wrap(s.ex, "exchange_rows", "exchange_rows"); wrap(s, "_bounds", "bounds(sync)"); wrap(s.ex, "exchange", "field_sync")
 tb, ts = 0.0, 0.0
 K = 10
