@@ -53,7 +53,7 @@ if rank == 0:
             scale = max(float(np.abs(cr[f]).max()), 1e-30)
             e[f] = float(np.abs(cs[f].astype(np.float64) - cr[f].astype(np.float64)).max() / scale)
         e["n"] = int(cs["pos"].shape[0])
-        ok = ok and cs["pos"].shape == cr["pos"].shape and e["pos"] <= 1e-5 and e["density"] <= 1e-5
+        ok = ok and cs["pos"].shape == cr["pos"].shape and e["pos"] <= 1e-5 and e["density"] <= 1e-5 and e["vel"] <= 2e-4
         out["steps"].append(e)
         ref.step()
     out["ok"] = bool(ok)
