@@ -199,7 +199,7 @@ class SlabSystem(SphkOps):
 
     HISTORY = {"dfsph": 1, "wcsph": 0, "pbd": 3}      # extra floats per particle that migrate with it
 
-    def __init__(self, scene, rank: int, world: int, device, capacity_factor: float = 1.35, group=None):
+    def __init__(self, scene, rank: int, world: int, device, capacity_factor: float = 1.6, group=None):
         self.L = capi.sphk()
         self.p = scene.params
         self.rank, self.world = rank, world
