@@ -107,6 +107,26 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel_substring: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the density kernel, from the committed
+    `ncu --set full` capture of this round (profiles/r01/sweeps_dfsph_2m.raw.csv); None if absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01", "sweeps_dfsph_2m.raw.csv")
+    if not os.path.exists(path):
+        return None, None
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        if kernel_substring in d.get("Kernel Name", ""):
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[hdr.index(k)], 1.0)
+                tot += float(d[k].replace(",", "")) * scale
+            return tot, os.path.relpath(path, ROOT)
+    return None, None
+
+
 def cpu_baseline(pkg, solver: str, budget_s: float = 25.0) -> dict:
     """The CPU restatement on a bounded sample of the workload: the same generator / constants / solver
     settings at the largest scene whose constructor (= step 0) + 1 step fit the budget."""
@@ -289,10 +309,13 @@ def run_ours_single(args, pkg) -> dict:
                         "alg_bytes_per_particle": None, "achieved_gbs": None, "frac": None, "share_of_step": float(np.mean(t)) / ms_step})
     dens = kernels[0]
     stats = s.list_stats()
+    traffic, traffic_src = ncu_traffic("OpDensityAlpha") if solver == "dfsph" and scene_name == "2m" else (None, None)
     roof = {"bound": "hbm", "kernel": dens["kernel"], "achieved": dens["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": dens["frac"], "traffic": None, "peak_source": peak_src,
+            "frac": dens["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "alg_bytes_per_launch": n * dens["alg_bytes_per_particle"], "ms_per_launch": dens["ms"], "kernels": kernels,
-            "note": "neighbour sweeps are bound by FP32 issue / L1 gather rate, not HBM (SURVEY 8d): see DESIGN.md"}
+            "note": "neighbour sweeps are bound by the L1 data pipe (scattered 32-byte-sector gathers) and FP32 issue, "
+                    "not by HBM (SURVEY 8d; ncu in profiles/): traffic exceeds the algorithmic bytes by the neighbour list "
+                    "streamed once per sweep"}
     if stats:
         roof["neighbors_per_particle"] = stats["total"] / n
     s.close()
