@@ -1,0 +1,523 @@
+// sphk_mg.cu -- multi-GPU slab support of libsphk: the neighbour exchanges of the x-slab decomposition
+// (the reference is single-GPU, so nothing here replaces reference code).
+//
+// One process per GPU.  A rank talks to its two x-neighbours only.  Two transports, both enqueued on the
+// context's stream with no host synchronisation:
+//
+//   * NCCL point-to-point (ncclSend/ncclRecv in one group), called natively.  NCCL is resolved with dlopen at
+//     run time -- inside a torch process that is torch's own libnccl.so.2 (same soname), so there is exactly one
+//     NCCL in the process; libsphk itself has no link-time NCCL dependency.  Used for the once-per-step
+//     candidate exchange (variable size, several arrays) and as the fallback halo transport.
+//
+//   * peer-memory mailboxes (CUDA IPC over NVLink / NVSwitch) for the ~21 per-sweep halos of a step:
+//     ONE kernel per halo stores this rank's first / last owned plane straight into the neighbours' mailboxes
+//     (remote stores), publishes a sequence flag, waits for the neighbours' flags on its own (local) mailboxes and
+//     unpacks them into the ghost slices of the API array AND the packed 32-byte records the sweeps gather
+//     (what sphk_push_range does after an NCCL halo).  No packing kernels, no NCCL launch latency, no extra
+//     record-mirror launches: 1 launch per halo instead of 3.
+//     Flow control: message k goes to mailbox k & 1.  A rank sends k+2 only after it has received k+1, which
+//     its neighbour sent after it had consumed k (stream order), so two mailboxes per direction suffice.
+//     Each message carries its element count: a mismatch between the owner's plane and the neighbour's ghost
+//     range raises a device-side error flag (read by sphk_mg_check) instead of hanging; waits are bounded.
+#include "sphk_internal.cuh"
+
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+
+// ---- the NCCL entry points this file uses (nccl.h 2.27: ncclUniqueId is 128 opaque bytes, passed by value) -------
+namespace {
+
+struct NcclUid { char internal[128]; };
+typedef void* NcclComm;
+enum { kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclInt32 = 2, kNcclSum = 0 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUid*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclUid, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.lib) return api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return api;
+    bool all = true;
+    auto sym = [&](const char* n) { void* p = dlsym(api.lib, n); if (!p) all = false; return p; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.ok = all;
+    return api;
+}
+
+// mailbox layout (per rank, one cudaMalloc, exported over CUDA IPC):
+//   box[side][parity] : Header (64 B) + capFloats floats        side 0 = written by the LEFT neighbour, 1 = by the RIGHT
+//   flag[side]        : unsigned long long, last sequence number the neighbour on that side has published
+struct MailHeader { int count; int pad[15]; };
+
+}  // namespace
+
+struct sphk_mg_comm {
+    int rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    NcclComm comm = nullptr;
+    int* dInts = nullptr;         // [4 * SPHK_MG_MAX_INTS] device staging of the small host exchanges
+    int* hInts = nullptr;         // pinned twin
+    double* dDouble = nullptr;
+    long long bytesSent = 0, messages = 0;
+    // ---- peer-memory mailboxes ----
+    size_t capFloats = 0;         // payload capacity of one mailbox
+    size_t boxBytes = 0;          // sizeof(MailHeader) + capFloats * 4, rounded to 256
+    unsigned char* mail = nullptr;        // this rank's mailboxes + flags (+ done counters, error word)
+    unsigned char* peer[2] = {nullptr, nullptr};   // neighbours' mailbox blocks, opened through IPC (0 = left, 1 = right)
+    bool connected = false;
+    unsigned long long seq = 0;   // halos issued through the mailboxes so far
+    int transport = 0;            // 0: NCCL halos, 1: mailbox halos
+};
+
+#define SPHK_MG_MAX_INTS 8
+
+namespace {
+
+int nccl_rc(int r) {
+    if (r == 0) return SPHK_OK;
+    std::fprintf(stderr, "sphk_mg: NCCL error %d (%s)\n", r, nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+    return SPHK_ERR_COMM;
+}
+#define SPHK_NCCL_TRY(expr) do { const int r_ = nccl_rc(expr); if (r_ != SPHK_OK) return r_; } while (0)
+
+inline size_t flags_offset(const sphk_mg_comm* m) { return 4 * m->boxBytes; }
+inline unsigned char* box_of(unsigned char* base, const sphk_mg_comm* m, int side, int parity) {
+    return base + (static_cast<size_t>(side) * 2 + parity) * m->boxBytes;
+}
+
+// words after the four boxes: flag[2] (ull), done[2] (uint), error (uint)
+struct MailTail { unsigned long long flag[2]; unsigned int done[2]; unsigned int error; unsigned int pad; };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct HaloSide {
+    const float* src;        // first float of the slice to send (nullptr: no neighbour on this side)
+    int sendFloats;          // floats to send
+    unsigned char* peerBox;  // neighbour's mailbox for this message (remote memory)
+    unsigned long long* peerFlag;   // neighbour's flag for messages from this rank (remote memory)
+    const unsigned char* myBox;     // this rank's mailbox the neighbour writes (local memory)
+    int ghostBegin, ghostCount;     // particles [ghostBegin, +ghostCount) receive the message
+};
+
+struct HaloArgs {
+    HaloSide side[2];
+    MailTail* tail;          // local
+    unsigned long long seq;
+    float* array;            // API array the ghost slices belong to (width floats per particle)
+    int width;               // 1 or 3
+    int what;                // sphk_push_range bit mask (0: array only)
+    Rec* rec;
+    const float4* posBuild;  // skin tracking (PBD position halos), or nullptr
+    unsigned int* dispMax;
+    unsigned long long timeoutNs;
+};
+
+constexpr int kHaloBlock = 256;
+
+// One halo: send both plane slices into the neighbours' mailboxes, publish, wait, unpack both ghost slices.
+// The grid is at most one block per SM (all blocks co-resident), so a block that waits never keeps a block that
+// still has to send from running.
+__global__ void __launch_bounds__(kHaloBlock) k_halo_mailbox(HaloArgs a) {
+    const int nthreads = gridDim.x * kHaloBlock;
+    const int tid = blockIdx.x * kHaloBlock + threadIdx.x;
+    // ---- 1. remote stores -------------------------------------------------------------------------------------
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const HaloSide& h = a.side[s];
+        if (!h.peerBox) continue;
+        float* dst = reinterpret_cast<float*>(h.peerBox + sizeof(MailHeader));
+        const float* src = h.src;
+        const int n = h.sendFloats;
+        // the slice starts at an arbitrary particle: peel to 16-byte alignment of the SOURCE, the mailbox payload is
+        // written with the same phase (payload offset = source misalignment), so both sides move float4s
+        const int lead = static_cast<int>((reinterpret_cast<uintptr_t>(src) >> 2) & 3);   // floats past a 16-byte boundary
+        const float* src0 = src - lead;
+        float* dst0 = dst;                        // dst[k] holds src0[k]; payload proper starts at dst + lead
+        const int total = n + lead;
+        const int nvec = total >> 2;
+        for (int v = tid; v < nvec; v += nthreads) {
+            const int k = v << 2;
+            if (k >= lead && k + 4 <= total) {
+                *reinterpret_cast<float4*>(dst0 + k) = __ldg(reinterpret_cast<const float4*>(src0 + k));
+            } else {
+                for (int j = 0; j < 4; ++j)
+                    if (k + j >= lead && k + j < total) dst0[k + j] = src0[k + j];
+            }
+        }
+        if (tid == 0) {
+            for (int k = nvec << 2; k < total; ++k)
+                if (k >= lead) dst0[k] = src0[k];
+            int* hdr = reinterpret_cast<int*>(h.peerBox);
+            hdr[0] = n; hdr[1] = lead;
+        }
+    }
+    // ---- 2. publish: the last block to finish its stores raises both neighbours' flags ----------------------------
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&a.tail->done[0], 1u);
+        if (prev == gridDim.x - 1) {
+            a.tail->done[0] = 0;
+            __threadfence_system();
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+                if (a.side[s].peerFlag) st_release_sys(a.side[s].peerFlag, a.seq);
+        }
+    }
+    // ---- 3. wait for the neighbours' messages (flags live in LOCAL memory), 4. unpack -------------------------------
+    __shared__ int sOk;
+    float d2 = 0.f;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const HaloSide& h = a.side[s];
+        if (!h.myBox) continue;
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = global_timer_ns();
+            int ok = (*reinterpret_cast<volatile unsigned int*>(&a.tail->error) & 3u) ? 0 : 1;   // an earlier wait timed out: do not stall again
+            while (ok && ld_acquire_sys(&a.tail->flag[s]) < a.seq) {
+                if (global_timer_ns() - t0 > a.timeoutNs) { ok = 0; atomicOr(&a.tail->error, 1u << s); break; }
+                __nanosleep(64);
+            }
+            sOk = ok;
+        }
+        __syncthreads();
+        const bool ok = sOk != 0;
+        __syncthreads();
+        if (!ok) continue;
+        const int* hdr = reinterpret_cast<const int*>(h.myBox);
+        const int n = __ldcg(hdr), lead = __ldcg(hdr + 1);
+        if (n != h.ghostCount * a.width) {            // ordering contract violated: report, do not touch memory
+            if (tid == 0) atomicOr(&a.tail->error, 4u << s);
+            continue;
+        }
+        const float* pay = reinterpret_cast<const float*>(h.myBox + sizeof(MailHeader)) + lead;
+        for (int t = tid; t < h.ghostCount; t += nthreads) {
+            const int i = h.ghostBegin + t;
+            if (a.width == 1) {
+                const float v = __ldcg(pay + t);
+                a.array[i] = v;
+                if (a.what & 2) a.rec[i].s = v;
+            } else {
+                const float3 v = f3(__ldcg(pay + 3 * t), __ldcg(pay + 3 * t + 1), __ldcg(pay + 3 * t + 2));
+                store3(a.array, i, v);
+                if (a.what & 1) rec_set_vel(a.rec + i, v);
+                if (a.what & 4) {
+                    rec_set_pos(a.rec + i, v);
+                    if (a.posBuild) { const float3 m = v - xyz(a.posBuild[i]); d2 = fmaxf(d2, dot3(m, m)); }
+                }
+            }
+        }
+    }
+    if ((a.what & 4) && a.posBuild) {        // ghosts moved by their owner count against the list skin (as k_push_range)
+        for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+        if ((threadIdx.x & 31) == 0 && __float_as_uint(d2) > *a.dispMax) atomicMax(a.dispMax, __float_as_uint(d2));
+    }
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 1;
+    }
+    return n;
+}
+
+}  // namespace
+
+// ---- lifetime ------------------------------------------------------------------------------------------------------
+extern "C" int sphk_mg_unique_id(unsigned char id[128]) {
+    if (!id) return SPHK_ERR_INVALID;
+    NcclApi& n = nccl();
+    if (!n.ok) return SPHK_ERR_COMM;
+    NcclUid u;
+    SPHK_NCCL_TRY(n.GetUniqueId(&u));
+    std::memcpy(id, u.internal, 128);
+    return SPHK_OK;
+}
+
+extern "C" int sphk_mg_init(sphk_mg_comm** out, int rank, int world, const unsigned char id[128], void* stream,
+                            long long mailbox_floats) {
+    if (!out || !id || world < 1 || rank < 0 || rank >= world || mailbox_floats < 0) return SPHK_ERR_INVALID;
+    *out = nullptr;
+    NcclApi& n = nccl();
+    if (!n.ok) return SPHK_ERR_COMM;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SPHK_ERR_NO_DEVICE;
+    sphk_mg_comm* m = new sphk_mg_comm();
+    m->rank = rank; m->world = world; m->stream = static_cast<cudaStream_t>(stream);
+    NcclUid u;
+    std::memcpy(u.internal, id, 128);
+    int rc = nccl_rc(n.CommInitRank(&m->comm, world, u, rank));
+    if (rc != SPHK_OK) { delete m; return rc; }
+    if (cudaMalloc(&m->dInts, 4 * SPHK_MG_MAX_INTS * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost(&m->hInts, 4 * SPHK_MG_MAX_INTS * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&m->dDouble, 2 * sizeof(double)) != cudaSuccess) {
+        delete m;
+        return SPHK_ERR_ALLOC;
+    }
+    if (mailbox_floats > 0) {
+        m->capFloats = static_cast<size_t>(mailbox_floats);
+        m->boxBytes = (sizeof(MailHeader) + (m->capFloats + 4) * sizeof(float) + 255) / 256 * 256;
+        const size_t total = 4 * m->boxBytes + sizeof(MailTail);
+        if (cudaMalloc(&m->mail, total) != cudaSuccess) { delete m; return SPHK_ERR_ALLOC; }
+        cudaMemset(m->mail, 0, total);
+        cudaDeviceSynchronize();
+    }
+    *out = m;
+    return SPHK_OK;
+}
+
+extern "C" void sphk_mg_destroy(sphk_mg_comm* m) {
+    if (!m) return;
+    cudaStreamSynchronize(m->stream);
+    for (int s = 0; s < 2; ++s)
+        if (m->peer[s]) cudaIpcCloseMemHandle(m->peer[s]);
+    if (m->comm) nccl().CommDestroy(m->comm);
+    cudaFree(m->mail);
+    cudaFree(m->dInts);
+    cudaFreeHost(m->hInts);
+    cudaFree(m->dDouble);
+    delete m;
+}
+
+// ---- mailbox wiring: handles travel by whatever side channel the caller has (torch.distributed all_gather) -------------
+extern "C" int sphk_mg_ipc_handle(sphk_mg_comm* m, unsigned char handle[64]) {
+    if (!m || !handle || !m->mail) return SPHK_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    SPHK_CUDA_TRY(cudaIpcGetMemHandle(&h, m->mail));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle, &h, 64);
+    return SPHK_OK;
+}
+
+extern "C" int sphk_mg_ipc_connect(sphk_mg_comm* m, const unsigned char* left64, const unsigned char* right64) {
+    if (!m || !m->mail) return SPHK_ERR_INVALID;
+    const unsigned char* hs[2] = {m->rank > 0 ? left64 : nullptr, m->rank < m->world - 1 ? right64 : nullptr};
+    for (int s = 0; s < 2; ++s) {
+        if ((s == 0 && m->rank > 0 && !left64) || (s == 1 && m->rank < m->world - 1 && !right64)) return SPHK_ERR_INVALID;
+        if (!hs[s]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, hs[s], 64);
+        void* p = nullptr;
+        SPHK_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        m->peer[s] = static_cast<unsigned char*>(p);
+    }
+    m->connected = true;
+    return SPHK_OK;
+}
+
+/* 0: NCCL halos, 1: mailbox halos (needs sphk_mg_ipc_connect on every rank) */
+extern "C" int sphk_mg_set_transport(sphk_mg_comm* m, int transport) {
+    if (!m || transport < 0 || transport > 1) return SPHK_ERR_INVALID;
+    if (transport == 1 && !(m->connected || m->world == 1)) return SPHK_ERR_STATE;
+    m->transport = transport;
+    return SPHK_OK;
+}
+
+// ---- small host-visible exchanges (synchronise the stream) ---------------------------------------------------------
+extern "C" int sphk_mg_exchange_ints(sphk_mg_comm* m, const int* to_left, const int* to_right, int* from_left, int* from_right,
+                                     int count) {
+    if (!m || count < 1 || count > SPHK_MG_MAX_INTS || !to_left || !to_right || !from_left || !from_right) return SPHK_ERR_INVALID;
+    NcclApi& n = nccl();
+    const int K = SPHK_MG_MAX_INTS;
+    for (int k = 0; k < count; ++k) { m->hInts[k] = to_left[k]; m->hInts[K + k] = to_right[k]; m->hInts[2 * K + k] = 0; m->hInts[3 * K + k] = 0; }
+    SPHK_CUDA_TRY(cudaMemcpyAsync(m->dInts, m->hInts, 4 * K * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    SPHK_NCCL_TRY(n.GroupStart());
+    if (m->rank > 0) {
+        SPHK_NCCL_TRY(n.Send(m->dInts, count, kNcclInt32, m->rank - 1, m->comm, m->stream));
+        SPHK_NCCL_TRY(n.Recv(m->dInts + 2 * K, count, kNcclInt32, m->rank - 1, m->comm, m->stream));
+    }
+    if (m->rank < m->world - 1) {
+        SPHK_NCCL_TRY(n.Send(m->dInts + K, count, kNcclInt32, m->rank + 1, m->comm, m->stream));
+        SPHK_NCCL_TRY(n.Recv(m->dInts + 3 * K, count, kNcclInt32, m->rank + 1, m->comm, m->stream));
+    }
+    SPHK_NCCL_TRY(n.GroupEnd());
+    SPHK_CUDA_TRY(cudaMemcpyAsync(m->hInts + 2 * K, m->dInts + 2 * K, 2 * K * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    SPHK_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    for (int k = 0; k < count; ++k) { from_left[k] = m->hInts[2 * K + k]; from_right[k] = m->hInts[3 * K + k]; }
+    return SPHK_OK;
+}
+
+extern "C" int sphk_mg_allreduce_sum(sphk_mg_comm* m, double* inout_host) {
+    if (!m || !inout_host) return SPHK_ERR_INVALID;
+    NcclApi& n = nccl();
+    SPHK_CUDA_TRY(cudaMemcpyAsync(m->dDouble, inout_host, sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    SPHK_NCCL_TRY(n.AllReduce(m->dDouble, m->dDouble + 1, 1, kNcclFloat64, kNcclSum, m->comm, m->stream));
+    SPHK_CUDA_TRY(cudaMemcpyAsync(inout_host, m->dDouble + 1, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    SPHK_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return SPHK_OK;
+}
+
+// ---- slice exchange over NCCL: for each array a, floats [begin*width, +count*width) ---------------------------------
+// send_left / send_right / recv_left / recv_right = {begin, count} in particles; one NCCL group on the stream.
+extern "C" int sphk_mg_exchange_slices(sphk_mg_comm* m, int narrays, const float* const* send_arrays, float* const* recv_arrays,
+                                       const int* widths, const int send_left[2], const int send_right[2],
+                                       const int recv_left[2], const int recv_right[2]) {
+    if (!m || narrays < 1 || !send_arrays || !recv_arrays || !widths || !send_left || !send_right || !recv_left || !recv_right)
+        return SPHK_ERR_INVALID;
+    NcclApi& n = nccl();
+    const bool L = m->rank > 0, R = m->rank < m->world - 1;
+    bool any = false;
+    for (int a = 0; a < narrays; ++a) {
+        const size_t w = static_cast<size_t>(widths[a]);
+        if (L && send_left[1] > 0) {
+            if (!any) { SPHK_NCCL_TRY(n.GroupStart()); any = true; }
+            SPHK_NCCL_TRY(n.Send(send_arrays[a] + send_left[0] * w, send_left[1] * w, kNcclFloat32, m->rank - 1, m->comm, m->stream));
+            m->bytesSent += static_cast<long long>(send_left[1] * w * 4); m->messages++;
+        }
+        if (L && recv_left[1] > 0) {
+            if (!any) { SPHK_NCCL_TRY(n.GroupStart()); any = true; }
+            SPHK_NCCL_TRY(n.Recv(recv_arrays[a] + recv_left[0] * w, recv_left[1] * w, kNcclFloat32, m->rank - 1, m->comm, m->stream));
+        }
+        if (R && send_right[1] > 0) {
+            if (!any) { SPHK_NCCL_TRY(n.GroupStart()); any = true; }
+            SPHK_NCCL_TRY(n.Send(send_arrays[a] + send_right[0] * w, send_right[1] * w, kNcclFloat32, m->rank + 1, m->comm, m->stream));
+            m->bytesSent += static_cast<long long>(send_right[1] * w * 4); m->messages++;
+        }
+        if (R && recv_right[1] > 0) {
+            if (!any) { SPHK_NCCL_TRY(n.GroupStart()); any = true; }
+            SPHK_NCCL_TRY(n.Recv(recv_arrays[a] + recv_right[0] * w, recv_right[1] * w, kNcclFloat32, m->rank + 1, m->comm, m->stream));
+        }
+    }
+    if (any) SPHK_NCCL_TRY(n.GroupEnd());
+    return SPHK_OK;
+}
+
+// ---- one halo: first / last owned plane -> the neighbours' ghost planes, then into the packed records ---------------------
+// ranges = {first_begin, first_count, last_begin, last_count, ghostL_begin, ghostL_count, ghostR_begin, ghostR_count}
+// what: sphk_push_range mask (1 vel: array = scene->fluid.vel, width 3; 2 scalar: width 1; 4 pos: array =
+// scene->fluid.pos, width 3) or 0 for an array no record mirrors (colour gradient, density, pressure).
+extern "C" int sphk_mg_halo(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, int what, float* array, int width, const int ranges[8]) {
+    if (!m || !c || !s || !array || !ranges || (width != 1 && width != 3) || (what != 0 && what != 1 && what != 2 && what != 4))
+        return SPHK_ERR_INVALID;
+    if ((what == 2 && width != 1) || ((what == 1 || what == 4) && width != 3)) return SPHK_ERR_INVALID;
+    for (int k = 0; k < 4; ++k)
+        if (ranges[2 * k] < 0 || ranges[2 * k + 1] < 0 || ranges[2 * k] + ranges[2 * k + 1] > c->nF) return SPHK_ERR_INVALID;
+    if (c->stream != m->stream) return SPHK_ERR_INVALID;
+    const bool L = m->rank > 0, R = m->rank < m->world - 1;
+    if (!L && !R) return SPHK_OK;
+    if (m->transport == 0) {
+        const float* sa[1] = {array};
+        float* ra[1] = {array};
+        const int w[1] = {width};
+        int rc = sphk_mg_exchange_slices(m, 1, sa, ra, w, ranges + 0, ranges + 2, ranges + 4, ranges + 6);
+        if (rc != SPHK_OK) return rc;
+        if (what) {
+            if (L && ranges[5] > 0) { rc = sphk_push_range(c, s, what, array, ranges[4], ranges[5]); if (rc != SPHK_OK) return rc; }
+            if (R && ranges[7] > 0) { rc = sphk_push_range(c, s, what, array, ranges[6], ranges[7]); if (rc != SPHK_OK) return rc; }
+        }
+        return SPHK_OK;
+    }
+    // ---- mailbox transport ----
+    if (!m->connected) return SPHK_ERR_STATE;
+    if (static_cast<size_t>(ranges[1]) * width > m->capFloats || static_cast<size_t>(ranges[3]) * width > m->capFloats ||
+        static_cast<size_t>(ranges[5]) * width > m->capFloats || static_cast<size_t>(ranges[7]) * width > m->capFloats)
+        return SPHK_ERR_CAPACITY;
+    const unsigned long long seq = ++m->seq;
+    const int parity = static_cast<int>(seq & 1);
+    MailTail* tail = reinterpret_cast<MailTail*>(m->mail + flags_offset(m));
+    HaloArgs a;
+    std::memset(&a, 0, sizeof(a));
+    // to the LEFT neighbour I am its RIGHT side (side index 1 in its block), and vice versa
+    if (L) {
+        MailTail* ptail = reinterpret_cast<MailTail*>(m->peer[0] + flags_offset(m));
+        a.side[0].src = array + static_cast<size_t>(ranges[0]) * width;
+        a.side[0].sendFloats = ranges[1] * width;
+        a.side[0].peerBox = box_of(m->peer[0], m, 1, parity);
+        a.side[0].peerFlag = &ptail->flag[1];
+        a.side[0].myBox = box_of(m->mail, m, 0, parity);
+        a.side[0].ghostBegin = ranges[4]; a.side[0].ghostCount = ranges[5];
+        m->bytesSent += static_cast<long long>(ranges[1]) * width * 4; m->messages++;
+    }
+    if (R) {
+        MailTail* ptail = reinterpret_cast<MailTail*>(m->peer[1] + flags_offset(m));
+        a.side[1].src = array + static_cast<size_t>(ranges[2]) * width;
+        a.side[1].sendFloats = ranges[3] * width;
+        a.side[1].peerBox = box_of(m->peer[1], m, 0, parity);
+        a.side[1].peerFlag = &ptail->flag[0];
+        a.side[1].myBox = box_of(m->mail, m, 1, parity);
+        a.side[1].ghostBegin = ranges[6]; a.side[1].ghostCount = ranges[7];
+        m->bytesSent += static_cast<long long>(ranges[3]) * width * 4; m->messages++;
+    }
+    a.tail = tail;
+    a.seq = seq;
+    a.array = array; a.width = width; a.what = what;
+    a.rec = c->rec;
+    const bool track = (what & 4) && c->listHasSkin && c->listEpoch == c->searchEpoch;
+    a.posBuild = track ? c->snapA : nullptr;
+    a.dispMax = c->dispMax;
+    a.timeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+    int work = ranges[1] > ranges[3] ? ranges[1] : ranges[3];
+    if (ranges[5] > work) work = ranges[5];
+    if (ranges[7] > work) work = ranges[7];
+    int blocks = (work * width / 4 + kHaloBlock - 1) / kHaloBlock;
+    if (blocks < 1) blocks = 1;
+    if (blocks > sm_count()) blocks = sm_count();
+    k_halo_mailbox<<<blocks, kHaloBlock, 0, c->stream>>>(a);
+    c->launches++;
+    if (what & 4) c->posDirty = true;
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+/* Reads the mailbox error word (synchronises the stream): 0 = fine; bit 0/1: timed out waiting for the left/right
+ * neighbour; bit 2/3: the message from the left/right neighbour did not match the ghost range. */
+extern "C" int sphk_mg_check(sphk_mg_comm* m, int* error_bits_host) {
+    if (!m || !error_bits_host) return SPHK_ERR_INVALID;
+    *error_bits_host = 0;
+    if (!m->mail) return SPHK_OK;
+    MailTail* tail = reinterpret_cast<MailTail*>(m->mail + flags_offset(m));
+    unsigned int e = 0;
+    SPHK_CUDA_TRY(cudaMemcpyAsync(&e, &tail->error, sizeof(e), cudaMemcpyDeviceToHost, m->stream));
+    SPHK_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    *error_bits_host = static_cast<int>(e);
+    return SPHK_OK;
+}
+
+extern "C" int sphk_mg_stats(const sphk_mg_comm* m, long long out_host[2]) {
+    if (!m || !out_host) return SPHK_ERR_INVALID;
+    out_host[0] = m->bytesSent; out_host[1] = m->messages;
+    return SPHK_OK;
+}

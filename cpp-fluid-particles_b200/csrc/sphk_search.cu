@@ -257,6 +257,7 @@ extern "C" const char* sphk_error_string(int code) {
     case SPHK_ERR_CAPACITY: return "sphk: particle count exceeds context capacity";
     case SPHK_ERR_STATE: return "sphk: call order violated (neighbour search missing or stale scene)";
     case SPHK_ERR_ALLOC: return "sphk: device allocation failed";
+    case SPHK_ERR_COMM: return "sphk: multi-GPU exchange failed (NCCL unavailable / error, or mailbox wiring missing)";
     default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "sphk: unknown error";
     }
 }

@@ -249,6 +249,11 @@ class SlabSystem(SphkOps):
                                  C.c_void_p(self.stream.cuda_stream)), "sphk_create")
         self._alloc_solver_buffers(cap)
         self.use_list = True
+        # native exchanges (csrc/sphk_mg.cu): NCCL called directly on the context stream + peer-memory mailboxes for
+        # the per-sweep halos.  The torch.distributed path below stays for gloo (CPU tests, ranks sharing one GPU).
+        self.mg = None
+        if world > 1 and not self.ex.stage and dist.get_backend(group) == "nccl" and os.environ.get("SPHK_SLAB_NATIVE", "1") == "1":
+            self._init_native(group, cap)
         # interior-first sweeps that overlap the halo exchange: implemented and parity-tested, but measured neutral at
         # N=2 (two extra small launches per sweep cost what the hidden exchange saves), hence opt-in
         self.overlap = os.environ.get("SPHK_SLAB_OVERLAP", "0") == "1"
@@ -264,6 +269,35 @@ class SlabSystem(SphkOps):
         self.step()                                     # the constructor's implicit step 0 (Q3)
 
     # ---- construction helpers --------------------------------------------------------------------------
+    def _init_native(self, group, cap):
+        """sphk_mg communicator: NCCL id from rank 0, mailbox IPC handles all-gathered (torch.distributed is the side
+        channel only), transport from SPHK_SLAB_TRANSPORT (1 = peer-memory mailboxes, default; 0 = NCCL halos)."""
+        L = self.L
+        ident = [None]
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            check(L.sphk_mg_unique_id(buf), "sphk_mg_unique_id")
+            ident[0] = bytes(buf)
+        dist.broadcast_object_list(ident, src=0, group=group)
+        transport = int(os.environ.get("SPHK_SLAB_TRANSPORT", "1"))
+        mailbox = 3 * max(262144, cap // 4) if transport == 1 else 0      # floats per message: 3 per plane particle
+        self.mg = C.c_void_p()
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(ident[0])
+        check(L.sphk_mg_init(C.byref(self.mg), C.c_int(self.rank), C.c_int(self.world), idbuf,
+                             C.c_void_p(self.stream.cuda_stream), C.c_longlong(mailbox)), "sphk_mg_init")
+        if transport == 1:
+            hb = (C.c_ubyte * 64)()
+            check(L.sphk_mg_ipc_handle(self.mg, hb), "sphk_mg_ipc_handle")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(hb), group=group)
+            hl = (C.c_ubyte * 64).from_buffer_copy(handles[self.rank - 1]) if self.rank > 0 else None
+            hr = (C.c_ubyte * 64).from_buffer_copy(handles[self.rank + 1]) if self.rank < self.world - 1 else None
+            check(L.sphk_mg_ipc_connect(self.mg, hl, hr), "sphk_mg_ipc_connect")
+            dist.barrier(group=group)                   # every mailbox is open before the first message
+        check(L.sphk_mg_set_transport(self.mg, C.c_int(transport)), "sphk_mg_set_transport")
+        self.transport = transport
+        self._cand_from = None
+
     def _global_boundary(self, scene):
         """Sorted global boundary positions + their masses (SPHSystem.cu:69-71) computed on this GPU."""
         p = self.p
@@ -307,11 +341,111 @@ class SlabSystem(SphkOps):
         self.search_fluid()
 
     def _bounds(self):
-        pc, w = self.plane_cells, self.w
-        idx = torch.tensor([0, pc, 2 * pc, 3 * pc, max(w - 1, 0) * pc, w * pc, (w + 1) * pc, (w + 2) * pc], device=self.device)
-        return tuple(self.cs_fluid[idx].cpu().tolist())
+        if not hasattr(self, "_bounds_idx"):
+            pc, w = self.plane_cells, self.w
+            self._bounds_idx = torch.tensor([0, pc, 2 * pc, 3 * pc, max(w - 1, 0) * pc, w * pc, (w + 1) * pc, (w + 2) * pc],
+                                            device=self.device)
+        return tuple(self.cs_fluid[self._bounds_idx].cpu().tolist())
+
+    def _exchange_ints(self, to_left, to_right):
+        k = len(to_left)
+        tl, tr = (C.c_int * k)(*to_left), (C.c_int * k)(*to_right)
+        fl, fr = (C.c_int * k)(), (C.c_int * k)()
+        check(self.L.sphk_mg_exchange_ints(self.mg, tl, tr, fl, fr, C.c_int(k)), "sphk_mg_exchange_ints")
+        return list(fl), list(fr)
+
+    def _swap_carried(self):
+        """The assembled set was received into the scratch twins: make them the live arrays (no copy back)."""
+        self.fluid.pos, self._alt[0] = self._alt[0], self.fluid.pos
+        self.fluid.vel, self._alt[1] = self._alt[1], self.fluid.vel
+        if self.solver == "dfsph":
+            self.warm, self._alt[2] = self._alt[2], self.warm
+        elif self.solver == "pbd":
+            self.pos_last, self._alt[2] = self._alt[2], self.pos_last
+        self._scene = None
+
+    def _begin_step_native(self):
+        """begin_step over csrc/sphk_mg.cu: candidates travel array by array in ONE NCCL group straight into their slots
+        of the assembled set (no packing, no copy back); the receive counts were agreed in the previous step, so the only
+        host synchronisation left is reading the plane offsets after the search."""
+        t0 = time.perf_counter()
+        L = self.L
+        arrays = self._carried()
+        if not hasattr(self, "_alt"):
+            self._alt = [torch.empty_like(a) for a in arrays]
+        if self._ranges is None:                         # very first step: as in begin_step below
+            self._search_all(self.n_own)
+            b = self._bounds()
+            if b[7] != self.n_own:
+                raise RuntimeError(f"slab rank {self.rank}: initial partition left particles outside the local grid")
+            r = plane_ranges(b, self.w)
+            r["own"] = (b[0], b[7])
+            r["to_left"] = (b[0], r["to_left"][1])
+            r["to_right"] = (r["to_right"][0], b[7])
+            self._ranges = r
+            fl, fr = self._exchange_ints([r["to_left"][1] - r["to_left"][0]], [r["to_right"][1] - r["to_right"][0]])
+            self._cand_from = (fl[0], fr[0])
+        r = self._ranges
+        nl, nr = self._cand_from
+        if self.ex.left is None:
+            nl = 0
+        if self.ex.right is None:
+            nr = 0
+        own0, own1 = r["own"]
+        n_own = own1 - own0
+        n_all = nl + n_own + nr
+        if n_all > self.cap:
+            raise RuntimeError(f"slab rank {self.rank}: capacity {self.cap} exceeded by {n_all} local particles")
+        k = len(arrays)
+        widths = (C.c_int * k)(*[1 if a.dim() == 1 else a.shape[1] for a in arrays])
+        src = (C.c_void_p * k)(*[a.data_ptr() for a in arrays])
+        dst = (C.c_void_p * k)(*[a.data_ptr() for a in self._alt])
+        i2 = C.c_int * 2
+        check(L.sphk_mg_exchange_slices(self.mg, C.c_int(k), src, dst, widths,
+                                        i2(r["to_left"][0], r["to_left"][1] - r["to_left"][0]),
+                                        i2(r["to_right"][0], r["to_right"][1] - r["to_right"][0]),
+                                        i2(0, nl), i2(nl + n_own, nr)), "sphk_mg_exchange_slices")
+        for a, d in zip(arrays, self._alt):
+            wd = 1 if a.dim() == 1 else a.shape[1]
+            check(L.sphk_copy(self.ctx, C.c_void_p(d.data_ptr() + 4 * wd * nl), C.c_void_p(a.data_ptr() + 4 * wd * own0),
+                              C.c_int(n_own * wd)), "sphk_copy")
+        self._swap_carried()
+        self._search_all(n_all)
+        b = self._bounds()
+        self._ranges = r = plane_ranges(b, self.w)
+        self.n_gl = r["ghost_l"][1] - r["ghost_l"][0]
+        self.n_own = r["own"][1] - r["own"][0]
+        self.n_gr = r["ghost_r"][1] - r["ghost_r"][0]
+        self.first_plane, self.last_plane = r["first"], r["last"]
+        self.ghost_l, self.ghost_r = r["ghost_l"], r["ghost_r"]
+        # one small exchange: (a) the ordering contract -- my ghost planes must be exactly the neighbours' boundary
+        # planes -- checked BEFORE any halo is posted (a mismatch would otherwise stall the exchange); (b) how many
+        # candidates each neighbour will send next step
+        n_first, n_last = self.first_plane[1] - self.first_plane[0], self.last_plane[1] - self.last_plane[0]
+        fl, fr = self._exchange_ints([n_first, r["to_left"][1] - r["to_left"][0]], [n_last, r["to_right"][1] - r["to_right"][0]])
+        if (self.ex.left is not None and fl[0] != self.n_gl) or (self.ex.right is not None and fr[0] != self.n_gr):
+            raise RuntimeError(f"slab rank {self.rank}: ghost planes {self.n_gl}/{self.n_gr} do not match the neighbours' "
+                               f"boundary planes {fl[0]}/{fr[0]} (a particle moved more than one plane in a step?)")
+        self._cand_from = (fl[1], fr[1])
+        err = C.c_int(0)
+        check(L.sphk_mg_check(self.mg, C.byref(err)), "sphk_mg_check")
+        if err.value:
+            raise RuntimeError(f"slab rank {self.rank}: halo mailbox error bits {err.value:#x} (see sphk_mg_check)")
+        self._halo_ranges = (C.c_int * 8)(self.first_plane[0], n_first, self.last_plane[0], n_last,
+                                          self.ghost_l[0], self.n_gl, self.ghost_r[0], self.n_gr)
+        check(L.sphk_set_active_range(self.ctx, C.c_int(r["own"][0]), C.c_int(self.n_own)))
+        if self.use_list:
+            self.set_use_list(True, 150 if self.solver == "pbd" else 0)
+            self.build_neighbor_list()
+        self.comm_s += time.perf_counter() - t0
+
+    def _halo(self, what: int, t: torch.Tensor):
+        check(self.L.sphk_mg_halo(self.mg, self.ctx, self._s(), C.c_int(what), _ptr(t), C.c_int(1 if t.dim() == 1 else t.shape[1]),
+                                  self._halo_ranges), "sphk_mg_halo")
 
     def begin_step(self):
+        if self.mg is not None:
+            return self._begin_step_native()
         t0 = time.perf_counter()
         arrays = self._carried()
         if not hasattr(self, "_alt"):
@@ -363,7 +497,7 @@ class SlabSystem(SphkOps):
         check(self.L.sphk_set_active_range(self.ctx, C.c_int(b), C.c_int(max(e - b, 0))))
 
     def _run(self, op, sync=None, tensor=None, split=True):
-        if sync is None or not split or not self.overlap or self.ex.stage:
+        if sync is None or not split or not self.overlap or self.ex.stage or self.mg is not None:
             return super()._run(op, sync, tensor)
         (f0, f1), (l0, l1) = self.first_plane, self.last_plane
         own0, own1 = self._ranges["own"]
@@ -397,18 +531,26 @@ class SlabSystem(SphkOps):
         return dist.batch_isend_irecv(ops) if ops else []
 
     def sync_vel(self):
+        if self.mg is not None:
+            return self._halo(1, self.fluid.vel)
         self._sync(self.fluid.vel)
         self._push(1, None)
 
     def sync_scalar(self, t):
+        if self.mg is not None:
+            return self._halo(2, t)
         self._sync(t)
         self._push(2, t)
 
     def sync_array(self, t):
+        if self.mg is not None:
+            return self._halo(0, t)
         self._sync(t)
 
     def sync_positions(self):
         """PBD moves positions inside a step (Q7): the ghosts follow their owners after every projection."""
+        if self.mg is not None:
+            return self._halo(4, self.fluid.pos)
         self._sync(self.fluid.pos)
         self._push(4, None)
 
@@ -421,6 +563,10 @@ class SlabSystem(SphkOps):
         return self._n_total
 
     def reduce_sum(self, x: float) -> float:
+        if self.mg is not None:
+            v = C.c_double(x)
+            check(self.L.sphk_mg_allreduce_sum(self.mg, C.byref(v)), "sphk_mg_allreduce_sum")
+            return float(v.value)
         t = torch.tensor([x], dtype=torch.float64, device=self.device)
         dist.all_reduce(t, group=self.ex.group)
         return float(t.item())
@@ -436,6 +582,21 @@ class SlabSystem(SphkOps):
 
     def n_global(self):
         return int(self.reduce_sum(float(self.n_own)))
+
+    def comm_stats(self):
+        """(bytes sent, messages sent) by this rank."""
+        if self.mg is not None:
+            out = (C.c_longlong * 2)()
+            check(self.L.sphk_mg_stats(self.mg, out))
+            return int(out[0]), int(out[1])
+        return self.ex.bytes_sent, self.ex.messages
+
+    def close(self):
+        if getattr(self, "mg", None) is not None and self.ctx:
+            self.L.sphk_synchronize(self.ctx)
+            self.L.sphk_mg_destroy(self.mg)
+            self.mg = None
+        super().close()
 
     def owned_state(self) -> dict:
         """Owned particles of this rank (host arrays)."""
@@ -501,7 +662,8 @@ def bench_main(args, pkg) -> dict | None:
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     comm = s.comm_s / args.steps
-    bytes_sent, msgs = s.ex.bytes_sent, s.ex.messages
+    bytes_sent, msgs = s.comm_stats()
+    transport = {None: "torch.distributed P2P", 0: "NCCL send/recv (native)", 1: "peer-memory mailboxes (CUDA IPC over NVLink) + NCCL candidates"}[getattr(s, "transport", None) if s.mg is not None else None]
     s.close()
     dist.destroy_process_group()
     if rank != 0:
@@ -512,7 +674,7 @@ def bench_main(args, pkg) -> dict | None:
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": B.workload_name(scene_name, solver), "n_fluid": n, "n_boundary": int(sc.boundary.shape[0]),
-                       "cells": list(sc.params.cell_size), "parallelism": f"x-slabs x{world}, halo = 1 cell plane, NCCL send/recv",
+                       "cells": list(sc.params.cell_size), "parallelism": f"x-slabs x{world}, halo = 1 cell plane, {transport}",
                        "per_gpu_particles_max": int(mx[0].item()), "load_imbalance": float(mx[0].item() * world / own[0].item()),
                        "l2": "inputs larger than L2 (packed records + neighbour list per rank > 126 MB); no flush"},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

@@ -40,7 +40,8 @@ enum {
     SPHK_ERR_NO_DEVICE = -2,  /* no CUDA device / driver: there is no CPU path */
     SPHK_ERR_CAPACITY = -3,   /* n exceeds the capacity given to sphk_create */
     SPHK_ERR_STATE = -4,      /* call order violated (e.g. sweep before neighbour search) */
-    SPHK_ERR_ALLOC = -5
+    SPHK_ERR_ALLOC = -5,
+    SPHK_ERR_COMM = -6        /* multi-GPU: NCCL missing / failed, or a neighbour's message did not arrive */
 };
 
 typedef struct sphk_ctx sphk_ctx;
@@ -204,16 +205,57 @@ int sphk_build_neighbor_list(sphk_ctx* ctx, const sphk_scene* s);
  * device buffers instead of a mapped GL vertex buffer; synchronises like the reference (vbo.cu:49). */
 int sphk_export_dots(sphk_ctx* ctx, const sphk_particles* p, float* dot_xyz, float* color_rgb);
 
-/* ---- multi-GPU slab support (no reference counterpart: the reference is single-GPU) ----------------
+/* ---- multi-GPU slab support (no reference counterpart: the reference is single-GPU; SURVEY 8e) ----------------
  * A slab rank keeps [ghost-left | owned | ghost-right] particles in one sorted set (cpp-fluid-particles_b200/
  * slabs.py).  Sweeps compute only the active (owned) range; ghost values arrive by halo exchange of the API
- * arrays (contiguous slices, sent with NCCL by the host) followed by sphk_push_range. */
+ * arrays (contiguous slices) and are mirrored into the packed records. */
 /* restrict every subsequent sweep to particles [begin, begin+count) of the fluid set (count<0: all) */
 int sphk_set_active_range(sphk_ctx* ctx, int begin, int count);
 /* copy API data of particles [begin, begin+count) into the packed records: what is a bit mask -- 1: vel
  * (scene->fluid.vel), 2: neighbour scalar from `array` (float[n]), 4: pos (scene->fluid.pos; PBD ghosts moved by
  * their owner: counted against the neighbour-list skin like local moves) */
 int sphk_push_range(sphk_ctx* ctx, const sphk_scene* s, int what, const float* array, int begin, int count);
+
+/* The exchanges themselves (csrc/sphk_mg.cu).  One sphk_mg_comm per rank = one process per GPU; a rank talks to
+ * ranks rank-1 ("left") and rank+1 ("right") only.  Everything is enqueued on the stream given to sphk_mg_init
+ * (must be the sphk_ctx stream) and nothing synchronises the host unless stated.  Transports:
+ *   NCCL point-to-point (resolved with dlopen at run time, so it is the process's one NCCL) for the once-per-step
+ *   candidate exchange and as fallback; peer-memory mailboxes over NVLink (CUDA IPC) for the per-sweep halos:
+ *   one kernel stores the boundary planes into the neighbours' memory, waits for theirs and unpacks them into the
+ *   ghost slices and the packed records. */
+typedef struct sphk_mg_comm sphk_mg_comm;
+/* rank 0 creates the NCCL id; ship the 128 bytes to every rank by any side channel */
+int  sphk_mg_unique_id(unsigned char id[128]);
+/* collective over all ranks.  mailbox_floats > 0 also allocates this rank's halo mailboxes (payload capacity per
+ * message, in floats) */
+int  sphk_mg_init(sphk_mg_comm** comm, int rank, int world, const unsigned char id[128], void* stream, long long mailbox_floats);
+void sphk_mg_destroy(sphk_mg_comm* comm);
+/* CUDA IPC handle of this rank's mailboxes (64 bytes) / open the neighbours' (NULL where there is none) */
+int  sphk_mg_ipc_handle(sphk_mg_comm* comm, unsigned char handle[64]);
+int  sphk_mg_ipc_connect(sphk_mg_comm* comm, const unsigned char* left_handle64, const unsigned char* right_handle64);
+/* halo transport: 0 = NCCL send/recv + sphk_push_range (default), 1 = peer-memory mailboxes (after ipc_connect) */
+int  sphk_mg_set_transport(sphk_mg_comm* comm, int transport);
+/* up to 8 ints to each neighbour and back (missing neighbour: zeros).  Synchronises the stream. */
+int  sphk_mg_exchange_ints(sphk_mg_comm* comm, const int* to_left, const int* to_right, int* from_left, int* from_right, int count);
+/* sum of one double over all ranks.  Synchronises the stream. */
+int  sphk_mg_allreduce_sum(sphk_mg_comm* comm, double* inout_host);
+/* NCCL: for every array a (widths[a] floats per particle) send particles send_left = {begin, count} of send_arrays[a]
+ * to the left rank and send_right to the right rank; receive recv_left / recv_right = {begin, count} of
+ * recv_arrays[a].  Counts must agree with the neighbours' (exchange them first).  One NCCL group. */
+int  sphk_mg_exchange_slices(sphk_mg_comm* comm, int narrays, const float* const* send_arrays, float* const* recv_arrays,
+                             const int* widths, const int send_left[2], const int send_right[2],
+                             const int recv_left[2], const int recv_right[2]);
+/* One halo of a per-particle API array (width 1 or 3 floats): ranges = {first_begin, first_count, last_begin,
+ * last_count, ghostL_begin, ghostL_count, ghostR_begin, ghostR_count} in particles -- the first / last owned plane go
+ * to the left / right rank, whose planes arrive in the ghost ranges and are mirrored into the packed records as
+ * sphk_push_range(what) would (what = 0: an array no record mirrors; 1: array = scene->fluid.vel; 2: neighbour
+ * scalar; 4: array = scene->fluid.pos). */
+int  sphk_mg_halo(sphk_mg_comm* comm, sphk_ctx* ctx, const sphk_scene* s, int what, float* array, int width, const int ranges[8]);
+/* mailbox error word (0 = fine; bit 0/1 timed out waiting for left/right; bit 2/3 size mismatch from left/right).
+ * Synchronises the stream. */
+int  sphk_mg_check(sphk_mg_comm* comm, int* error_bits_host);
+/* {bytes sent, messages sent} by this rank so far */
+int  sphk_mg_stats(const sphk_mg_comm* comm, long long out_host[2]);
 
 /* ---- introspection for parity tests --------------------------------------------------------- */
 /* copies the stable-sort permutation of the last fluid search (perm[s] = pre-sort index) to device

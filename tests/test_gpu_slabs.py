@@ -12,11 +12,12 @@ from util import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _run(nproc, extra, timeout=600):
+def _run(nproc, extra, timeout=600, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + nproc + len(extra)),
            os.path.join(ROOT, "tools", "slab_check.py")] + extra
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, cwd=ROOT)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, cwd=ROOT,
+                       env=dict(os.environ, **(env or {})))
     line = [l for l in r.stdout.splitlines() if l.startswith("SLAB_CHECK ")]
     assert r.returncode == 0 and line, r.stdout[-3000:]
     return json.loads(line[-1][len("SLAB_CHECK "):])
@@ -33,9 +34,17 @@ def test_slabs_match_single_gpu_shared_device(built, solver, world):
     assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
 
 
-def test_slabs_match_single_gpu_nccl(built):
+@pytest.mark.parametrize("solver", ["dfsph", "wcsph", "pbd"])
+@pytest.mark.parametrize("transport", ["mailbox", "nccl", "torch"])
+def test_slabs_match_single_gpu_nccl(built, solver, transport):
+    """One rank per GPU over NVLink: the native exchanges of csrc/sphk_mg.cu (peer-memory mailbox halos / NCCL halos)
+    and the torch.distributed path must all reproduce the single-GPU result."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
-    out = _run(2, ["--backend", "nccl", "--solver", "dfsph", "--steps", "3"])
+    env = {"mailbox": {"SPHK_SLAB_NATIVE": "1", "SPHK_SLAB_TRANSPORT": "1"},
+           "nccl": {"SPHK_SLAB_NATIVE": "1", "SPHK_SLAB_TRANSPORT": "0"},
+           "torch": {"SPHK_SLAB_NATIVE": "0"}}[transport]
+    out = _run(2, ["--backend", "nccl", "--solver", solver, "--steps", "3", "--jitter", "0.001"], timeout=100, env=env)
     assert out["ok"], out
+    assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
