@@ -252,6 +252,8 @@ class SlabSystem(SphkOps):
         # native exchanges (csrc/sphk_mg.cu): NCCL called directly on the context stream + peer-memory mailboxes for
         # the per-sweep halos.  The torch.distributed path below stays for gloo (CPU tests, ranks sharing one GPU).
         self.mg = None
+        self.time_assembly = False
+        self._assembly_events = []
         if world > 1 and not self.ex.stage and dist.get_backend(group) == "nccl" and os.environ.get("SPHK_SLAB_NATIVE", "1") == "1":
             self._init_native(group, cap)
         # interior-first sweeps that overlap the halo exchange: implemented and parity-tested, but measured neutral at
@@ -370,6 +372,10 @@ class SlabSystem(SphkOps):
         host synchronisation left is reading the plane offsets after the search."""
         t0 = time.perf_counter()
         L = self.L
+        ev = None
+        if self.time_assembly:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         arrays = self._carried()
         if not hasattr(self, "_alt"):
             self._alt = [torch.empty_like(a) for a in arrays]
@@ -437,7 +443,19 @@ class SlabSystem(SphkOps):
         if self.use_list:
             self.set_use_list(True, 150 if self.solver == "pbd" else 0)
             self.build_neighbor_list()
+        if ev is not None:
+            ev[1].record()
+            self._assembly_events.append(ev)
         self.comm_s += time.perf_counter() - t0
+
+    def assembly_ms(self) -> float:
+        """Device time (CUDA events) of the recorded begin_step phases: candidate exchange + search + plane offsets +
+        count exchange + list build, host round trips included.  Synchronises."""
+        torch.cuda.synchronize(self.device)
+        ms = sum(a.elapsed_time(b) for a, b in self._assembly_events)
+        n = max(len(self._assembly_events), 1)
+        self._assembly_events = []
+        return ms / n
 
     def _halo(self, what: int, t: torch.Tensor):
         check(self.L.sphk_mg_halo(self.mg, self.ctx, self._s(), C.c_int(what), _ptr(t), C.c_int(1 if t.dim() == 1 else t.shape[1]),
@@ -643,6 +661,7 @@ def bench_main(args, pkg) -> dict | None:
         sampler.start()
     launches0 = s.launch_count()
     s.comm_s = 0.0
+    s.time_assembly = s.mg is not None
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -662,6 +681,7 @@ def bench_main(args, pkg) -> dict | None:
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     comm = s.comm_s / args.steps
+    assembly_ms = s.assembly_ms() if s.mg is not None else None
     bytes_sent, msgs = s.comm_stats()
     transport = {None: "torch.distributed P2P", 0: "NCCL send/recv (native)", 1: "peer-memory mailboxes (CUDA IPC over NVLink) + NCCL candidates"}[getattr(s, "transport", None) if s.mg is not None else None]
     s.close()
@@ -679,6 +699,9 @@ def bench_main(args, pkg) -> dict | None:
                        "l2": "inputs larger than L2 (packed records + neighbour list per rank > 126 MB); no flush"},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "note": "multi-GPU run is device-resident; the host-buffer e2e path is measured at N=1"},
-            "gpu_launches": int(launches.item()), "halo": {"host_seconds_per_step_in_assembly": comm,
+            "gpu_launches": int(launches.item()), "halo": {"assembly_ms_per_step_device": assembly_ms,
+                                                           "assembly_note": "candidate exchange + search of [ghosts|owned] + plane offsets (host read) + count "
+                                                                            "exchange + list build, CUDA events on rank 0; the rest of the step is sweeps + one halo kernel each",
+                                                           "host_wall_seconds_per_step_in_begin_step": comm,
                                                            "bytes_sent_rank0_total": bytes_sent, "messages_rank0_total": msgs},
             "clocks": clocks}
