@@ -72,9 +72,14 @@ NcclApi& nccl() {
 }
 
 // mailbox layout (per rank, one cudaMalloc, exported over CUDA IPC):
+//   info              : MailInfo (256 B): magic + payload capacity, so a neighbour can check that both sides agree on
+//                       the layout before it computes addresses inside this block
 //   box[side][parity] : Header (64 B) + capFloats floats        side 0 = written by the LEFT neighbour, 1 = by the RIGHT
-//   flag[side]        : unsigned long long, last sequence number the neighbour on that side has published
+//   tail              : flag[side] = last sequence number the neighbour on that side has published; done counter; error word
 struct MailHeader { int count; int pad[15]; };
+struct MailInfo { unsigned long long magic; unsigned long long capFloats; unsigned long long boxBytes; unsigned char pad[232]; };
+static_assert(sizeof(MailInfo) == 256, "MailInfo is one 256-byte block");
+constexpr unsigned long long kMailMagic = 0x5350484b4d41494cull;   // "SPHKMAIL"
 
 }  // namespace
 
@@ -107,9 +112,9 @@ int nccl_rc(int r) {
 }
 #define SPHK_NCCL_TRY(expr) do { const int r_ = nccl_rc(expr); if (r_ != SPHK_OK) return r_; } while (0)
 
-inline size_t flags_offset(const sphk_mg_comm* m) { return 4 * m->boxBytes; }
+inline size_t flags_offset(const sphk_mg_comm* m) { return sizeof(MailInfo) + 4 * m->boxBytes; }
 inline unsigned char* box_of(unsigned char* base, const sphk_mg_comm* m, int side, int parity) {
-    return base + (static_cast<size_t>(side) * 2 + parity) * m->boxBytes;
+    return base + sizeof(MailInfo) + (static_cast<size_t>(side) * 2 + parity) * m->boxBytes;
 }
 
 // words after the four boxes: flag[2] (ull), done[2] (uint), error (uint)
@@ -300,9 +305,13 @@ extern "C" int sphk_mg_init(sphk_mg_comm** out, int rank, int world, const unsig
     if (mailbox_floats > 0) {
         m->capFloats = static_cast<size_t>(mailbox_floats);
         m->boxBytes = (sizeof(MailHeader) + (m->capFloats + 4) * sizeof(float) + 255) / 256 * 256;
-        const size_t total = 4 * m->boxBytes + sizeof(MailTail);
+        const size_t total = sizeof(MailInfo) + 4 * m->boxBytes + 256;
         if (cudaMalloc(&m->mail, total) != cudaSuccess) { delete m; return SPHK_ERR_ALLOC; }
         cudaMemset(m->mail, 0, total);
+        MailInfo info;
+        std::memset(&info, 0, sizeof(info));
+        info.magic = kMailMagic; info.capFloats = m->capFloats; info.boxBytes = m->boxBytes;
+        cudaMemcpy(m->mail, &info, sizeof(info), cudaMemcpyHostToDevice);
         cudaDeviceSynchronize();
     }
     *out = m;
@@ -343,6 +352,14 @@ extern "C" int sphk_mg_ipc_connect(sphk_mg_comm* m, const unsigned char* left64,
         void* p = nullptr;
         SPHK_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         m->peer[s] = static_cast<unsigned char*>(p);
+        // every address inside the neighbour's block is computed from MY boxBytes: refuse a neighbour laid out differently
+        MailInfo info;
+        SPHK_CUDA_TRY(cudaMemcpy(&info, p, sizeof(info), cudaMemcpyDefault));
+        if (info.magic != kMailMagic || info.capFloats != m->capFloats || info.boxBytes != m->boxBytes) {
+            std::fprintf(stderr, "sphk_mg: rank %d: neighbour mailbox capacity %llu floats differs from mine (%zu): every rank must "
+                                 "pass the same mailbox_floats to sphk_mg_init\n", m->rank, info.capFloats, m->capFloats);
+            return SPHK_ERR_INVALID;
+        }
     }
     m->connected = true;
     return SPHK_OK;

@@ -35,6 +35,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import time
 
 import numpy as np
@@ -219,6 +220,7 @@ class SlabSystem(SphkOps):
         self.x0, self.x1, self.w = x0, x1, x1 - x0
         mine = scene.fluid[(plane >= x0) & (plane < x1)]
         n_total = scene.fluid.shape[0]
+        self._n_scene_fluid = n_total
         cap = int(max(mine.shape[0], n_total / world) * capacity_factor) + 4096
         self.cap = cap
         # ---- boundary: masses from the GLOBAL boundary set (every rank computes them once), then the subset
@@ -282,20 +284,41 @@ class SlabSystem(SphkOps):
             ident[0] = bytes(buf)
         dist.broadcast_object_list(ident, src=0, group=group)
         transport = int(os.environ.get("SPHK_SLAB_TRANSPORT", "1"))
-        mailbox = 3 * max(262144, cap // 4) if transport == 1 else 0      # floats per message: 3 per plane particle
+        # floats per message (3 per plane particle).  Derived from GLOBAL quantities only: every rank must use the same
+        # capacity, because a rank computes addresses inside its neighbours' mailboxes from its own layout
+        mailbox = 3 * max(262144, int(self._n_scene_fluid / self.world * 1.6) // 4) if transport == 1 else 0
         self.mg = C.c_void_p()
         idbuf = (C.c_ubyte * 128).from_buffer_copy(ident[0])
         check(L.sphk_mg_init(C.byref(self.mg), C.c_int(self.rank), C.c_int(self.world), idbuf,
                              C.c_void_p(self.stream.cuda_stream), C.c_longlong(mailbox)), "sphk_mg_init")
         if transport == 1:
-            hb = (C.c_ubyte * 64)()
-            check(L.sphk_mg_ipc_handle(self.mg, hb), "sphk_mg_ipc_handle")
+            # wiring can fail on one rank only (no peer access, IPC disabled in the container ...): the ranks agree on the
+            # outcome and ALL fall back to NCCL halos together -- mixed transports would wait for each other forever
+            ok, why = True, ""
+            try:
+                hb = (C.c_ubyte * 64)()
+                check(L.sphk_mg_ipc_handle(self.mg, hb), "sphk_mg_ipc_handle")
+            except RuntimeError as e:
+                ok, why, hb = False, str(e), (C.c_ubyte * 64)()
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(hb), group=group)
-            hl = (C.c_ubyte * 64).from_buffer_copy(handles[self.rank - 1]) if self.rank > 0 else None
-            hr = (C.c_ubyte * 64).from_buffer_copy(handles[self.rank + 1]) if self.rank < self.world - 1 else None
-            check(L.sphk_mg_ipc_connect(self.mg, hl, hr), "sphk_mg_ipc_connect")
-            dist.barrier(group=group)                   # every mailbox is open before the first message
+            dist.all_gather_object(handles, (bytes(hb), mailbox, ok), group=group)
+            if any(h[1] != mailbox for h in handles):
+                raise RuntimeError(f"slab rank {self.rank}: mailbox capacities differ across ranks: {[h[1] for h in handles]}")
+            if all(h[2] for h in handles):
+                hl = (C.c_ubyte * 64).from_buffer_copy(handles[self.rank - 1][0]) if self.rank > 0 else None
+                hr = (C.c_ubyte * 64).from_buffer_copy(handles[self.rank + 1][0]) if self.rank < self.world - 1 else None
+                try:
+                    check(L.sphk_mg_ipc_connect(self.mg, hl, hr), "sphk_mg_ipc_connect")
+                except RuntimeError as e:
+                    ok, why = False, str(e)
+            else:
+                ok = False
+            oks = [None] * self.world
+            dist.all_gather_object(oks, ok, group=group)   # also: every mailbox is open before the first message
+            if not all(oks):
+                if self.rank == 0:
+                    print(f"[slabs] peer-memory mailboxes unavailable ({why or 'on another rank'}): NCCL halos instead", file=sys.stderr, flush=True)
+                transport = 0
         check(L.sphk_mg_set_transport(self.mg, C.c_int(transport)), "sphk_mg_set_transport")
         self.transport = transport
         self._cand_from = None
@@ -653,6 +676,25 @@ def bench_main(args, pkg) -> dict | None:
     scene_name = args.scene or B.SCENE_OF_N[world]
     sc = pkg.scene.benchmark_scene(scene_name, solver)
     n = sc.fluid.shape[0]
+    # a rank that dies must take the job down at once (its neighbours would wait for it inside a collective), and a job
+    # that stops making progress must not sit on the GPUs: bounded by a watchdog
+    import threading
+    limit = float(os.environ.get("SPHK_BENCH_WATCHDOG_S", "420"))
+    dog = threading.Timer(limit, lambda: (print(f"[bench] rank {rank}: no result after {limit:.0f} s, aborting", file=sys.stderr, flush=True), os._exit(3)))
+    dog.daemon = True
+    dog.start()
+    try:
+        return _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name)
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush(); sys.stdout.flush()
+        os._exit(1)
+    finally:
+        dog.cancel()
+
+
+def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
     s = SlabSystem(sc, rank, world, torch.device("cuda", local))
     for _ in range(args.warmup):
         s.step()
@@ -680,7 +722,51 @@ def bench_main(args, pkg) -> dict | None:
     dist.all_reduce(own)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
-    comm = s.comm_s / args.steps
+    # ---- e2e: every step takes this rank's owned particles from pinned HOST buffers and returns them there ------------
+    # (pos + vel in, pos + vel + density out; copies on the compute stream, inside the timed region)
+    e2e = None
+    try:
+        cap = s.cap
+        hpos = torch.empty((cap, 3), dtype=torch.float32, pin_memory=True)
+        hvel = torch.empty((cap, 3), dtype=torch.float32, pin_memory=True)
+        hden = torch.empty(cap, dtype=torch.float32, pin_memory=True)
+
+        def down():
+            a, b = s._ranges["own"]
+            hpos[:b - a].copy_(s.fluid.pos[a:b], non_blocking=True)
+            hvel[:b - a].copy_(s.fluid.vel[a:b], non_blocking=True)
+            hden[:b - a].copy_(s.fluid.density[a:b], non_blocking=True)
+            return 28 * (b - a)
+
+        def up():
+            a, b = s._ranges["own"]
+            s.fluid.pos[a:b].copy_(hpos[:b - a], non_blocking=True)
+            s.fluid.vel[a:b].copy_(hvel[:b - a], non_blocking=True)
+            return 24 * (b - a)
+
+        down()
+        torch.cuda.synchronize()
+        k2 = max(3, args.steps // 2)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h2d = d2h = 0
+        f0.record()
+        for _ in range(k2):
+            h2d += up()
+            s.step()
+            d2h += down()
+        f1.record()
+        torch.cuda.synchronize()
+        e2e = (f0.elapsed_time(f1) / k2, h2d / k2, d2h / k2)
+    except Exception as exc:                               # the device-resident line above stays valid
+        print(f"[bench] rank {rank}: e2e leg failed: {exc}", file=sys.stderr, flush=True)
+    t = torch.tensor([e2e[0] if e2e else -1.0, 0.0 if e2e else 1.0, e2e[1] if e2e else 0.0, e2e[2] if e2e else 0.0],
+                     dtype=torch.float64, device=s.device)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)            # slowest rank; any failure flags the leg
+    dist.all_reduce(t)                                      # bytes summed over ranks
+    e2e_ms, e2e_failed = float(tmax[0].item()), bool(tmax[1].item() > 0)
+    e2e_h2d, e2e_d2h = int(t[2].item()), int(t[3].item())
+    comm = s.comm_s / (args.steps + (0 if e2e is None else max(3, args.steps // 2)))
     assembly_ms = s.assembly_ms() if s.mg is not None else None
     bytes_sent, msgs = s.comm_stats()
     transport = {None: "torch.distributed P2P", 0: "NCCL send/recv (native)", 1: "peer-memory mailboxes (CUDA IPC over NVLink) + NCCL candidates"}[getattr(s, "transport", None) if s.mg is not None else None]
@@ -697,8 +783,13 @@ def bench_main(args, pkg) -> dict | None:
                        "cells": list(sc.params.cell_size), "parallelism": f"x-slabs x{world}, halo = 1 cell plane, {transport}",
                        "per_gpu_particles_max": int(mx[0].item()), "load_imbalance": float(mx[0].item() * world / own[0].item()),
                        "l2": "inputs larger than L2 (packed records + neighbour list per rank > 126 MB); no flush"},
-            "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "multi-GPU run is device-resident; the host-buffer e2e path is measured at N=1"},
+            "e2e": ({"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                     "note": "e2e leg failed on a rank; device-resident value repeated"} if e2e_failed else
+                    {"value": n / (e2e_ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": e2e_ms,
+                     "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h, "steps": max(3, args.steps // 2),
+                     "api": "SlabSystem.step() per rank; every step uploads the rank's owned pos+vel from pinned host buffers "
+                            "and downloads pos+vel+density into them (bytes summed over ranks)",
+                     "timer": "CUDA events on the compute stream (copies are enqueued on it), max over ranks"}),
             "gpu_launches": int(launches.item()), "halo": {"assembly_ms_per_step_device": assembly_ms,
                                                            "assembly_note": "candidate exchange + search of [ghosts|owned] + plane offsets (host read) + count "
                                                                             "exchange + list build, CUDA events on rank 0; the rest of the step is sweeps + one halo kernel each",

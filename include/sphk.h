@@ -227,7 +227,7 @@ typedef struct sphk_mg_comm sphk_mg_comm;
 /* rank 0 creates the NCCL id; ship the 128 bytes to every rank by any side channel */
 int  sphk_mg_unique_id(unsigned char id[128]);
 /* collective over all ranks.  mailbox_floats > 0 also allocates this rank's halo mailboxes (payload capacity per
- * message, in floats) */
+ * message, in floats; MUST be the same number on every rank -- sphk_mg_ipc_connect checks it) */
 int  sphk_mg_init(sphk_mg_comm** comm, int rank, int world, const unsigned char id[128], void* stream, long long mailbox_floats);
 void sphk_mg_destroy(sphk_mg_comm* comm);
 /* CUDA IPC handle of this rank's mailboxes (64 bytes) / open the neighbours' (NULL where there is none) */
