@@ -114,16 +114,19 @@ def ncu_traffic(kernel_substring: str):
     path = os.path.join(ROOT, "profiles", "r01", "sweeps_dfsph_2m.raw.csv")
     if not os.path.exists(path):
         return None, None
-    rows = list(csv.reader(open(path)))
-    hdr, units = rows[0], rows[1]
-    for r in rows[2:]:
-        d = dict(zip(hdr, r))
-        if kernel_substring in d.get("Kernel Name", ""):
-            tot = 0.0
-            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[hdr.index(k)], 1.0)
-                tot += float(d[k].replace(",", "")) * scale
-            return tot, os.path.relpath(path, ROOT)
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            if kernel_substring in d.get("Kernel Name", ""):
+                tot = 0.0
+                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[hdr.index(k)], 1.0)
+                    tot += float(d[k].replace(",", "")) * scale
+                return tot, os.path.relpath(path, ROOT)
+    except (OSError, ValueError, KeyError, IndexError):
+        pass                                    # a malformed capture must not take the bench line down
     return None, None
 
 
@@ -326,7 +329,7 @@ def run_ours_single(args, pkg) -> dict:
     pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()  # noqa: E731
     hpos, hvel, hden = pin((n, 3)), pin((n, 3)), pin((n,))
     app.download_into(hpos, hvel, hden)
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(3, args.warmup)):     # (the class layer captures its step graph in its third plain step: keep that out of the timed region)
         app.upload(hpos, hvel); app.step(); app.download_into(hpos, hvel, hden)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
