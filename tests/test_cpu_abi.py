@@ -70,3 +70,25 @@ def test_product_never_imports_oracle():
                     if re.search(r"(from|import)\s+oracle|liboracle|oracle/sph_oracle", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_mg_entry_points_validate_arguments(pkg, built):
+    """The multi-GPU exchanges (csrc/sphk_mg.cu) reject bad arguments and, like sphk_create, refuse to run without a
+    device -- no compute here."""
+    import torch
+    from cpp_fluid_particles_b200 import capi
+    L = capi.sphk()
+    ident = (C.c_ubyte * 128)()
+    comm = C.c_void_p()
+    assert L.sphk_mg_init(C.byref(comm), 3, 2, ident, None, C.c_longlong(0)) == -1      # rank >= world
+    assert L.sphk_mg_init(None, 0, 1, ident, None, C.c_longlong(0)) == -1
+    assert L.sphk_mg_halo(None, None, None, 0, None, 1, None) == -1
+    assert L.sphk_mg_exchange_ints(None, None, None, None, None, 1) == -1
+    assert L.sphk_mg_exchange_slices(None, 1, None, None, None, None, None, None, None) == -1
+    assert L.sphk_mg_set_transport(None, 1) == -1
+    assert L.sphk_mg_check(None, None) == -1
+    L.sphk_mg_destroy(None)                                                             # no-op
+    assert b"multi-GPU" in L.sphk_error_string(-6)
+    if not torch.cuda.is_available():
+        rc = L.sphk_mg_init(C.byref(comm), 0, 1, ident, None, C.c_longlong(0))
+        assert rc in (-2, -6) and not comm.value      # no device (or no NCCL library): fails loudly, nothing created
