@@ -3,6 +3,8 @@
   cpp-fluid-particles_b200/libsphk.so     nvcc, sm_100a: CUDA kernels + the C-ABI (include/sphk.h)
   cpp-fluid-particles_b200/libsphhost.so  g++: reference-shaped C++ classes + headless facade
                                           (include/sph_app.h), linked against libsphk.so
+  cpp-fluid-particles_b200/sph_headless   g++: the reference application without its window (app/sph_headless.cpp),
+                                          linked against the two libraries
 """
 from __future__ import annotations
 
@@ -23,6 +25,8 @@ CUDA_LIB = "/usr/local/cuda/lib64"
 
 LIBSPHK = os.path.join(HERE, "libsphk.so")
 LIBHOST = os.path.join(HERE, "libsphhost.so")
+APP = os.path.join(HERE, "app")
+CLI = os.path.join(HERE, "sph_headless")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-use_fast_math",
               "-Xcompiler", "-fPIC", "-I" + INC, "-I" + CSRC]
@@ -79,9 +83,20 @@ def build_host(force: bool = False) -> str:
     return LIBHOST
 
 
+def build_cli(force: bool = False) -> str:
+    src = os.path.join(APP, "sph_headless.cpp")
+    deps = [src, LIBHOST, LIBSPHK] + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".h", ".hpp"))]
+    if not force and _newer(CLI, deps):
+        return CLI
+    _run([CXX, "-std=c++17", "-O2", "-Wall", "-I" + INC, "-I" + HOST, "-I" + CUDA_INC, "-o", CLI, src,
+          "-L" + HERE, "-lsphhost", "-lsphk", "-L" + CUDA_LIB, "-lcudart", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + CUDA_LIB])
+    return CLI
+
+
 def build_all(force: bool = False) -> None:
     build_sphk(force)
     build_host(force)
+    build_cli(force)
 
 
 if __name__ == "__main__":

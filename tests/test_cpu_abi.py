@@ -92,3 +92,28 @@ def test_mg_entry_points_validate_arguments(pkg, built):
     if not torch.cuda.is_available():
         rc = L.sphk_mg_init(C.byref(comm), 0, 1, ident, None, C.c_longlong(0))
         assert rc in (-2, -6) and not comm.value      # no device (or no NCCL library): fails loudly, nothing created
+
+
+def test_headless_cli_scene_matches_benchmark_scenes_and_fails_loudly(pkg, built, tmp_path):
+    """app/sph_headless.cpp (the reference application without its window): its C++ scene generator
+    reproduces the python generator the benchmarks use bit for bit, and without a GPU it refuses to run."""
+    import subprocess
+    import numpy as np
+    import torch
+    cli = os.path.join(ROOT, "cpp-fluid-particles_b200", "sph_headless")
+    assert os.path.exists(cli)
+    cases = [("config0", []),
+             ("slabtest", ["--box", "2.0", "1.0", "1.0", "--block", "64", "24", "24", "--origin", "0.285", "0.105", "0.285"])]
+    for name, args in cases:
+        pre = str(tmp_path / name)
+        r = subprocess.run([cli, "--emit-scene", pre] + args, capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, r.stderr
+        sc = pkg.scene.make_scene(name)
+        assert f"{list(int(c) for c in sc.params.cell_size)}" in r.stdout
+        fl = np.fromfile(pre + ".fluid.f32", np.float32).reshape(-1, 3)
+        bd = np.fromfile(pre + ".boundary.f32", np.float32).reshape(-1, 3)
+        assert np.array_equal(fl, sc.fluid) and np.array_equal(bd, sc.boundary), name
+    if not torch.cuda.is_available():
+        r = subprocess.run([cli, "--frames", "1"], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 3 and "no CPU path" in r.stderr
+    assert subprocess.run([cli, "--solver", "nonsense"], capture_output=True, timeout=60).returncode == 2
