@@ -34,8 +34,8 @@ def test_slabs_match_single_gpu_shared_device(built, solver, world):
     assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
 
 
-@pytest.mark.parametrize("solver", ["dfsph", "wcsph", "pbd"])
-@pytest.mark.parametrize("transport", ["mailbox", "nccl", "torch"])
+@pytest.mark.parametrize("transport,solver", [("mailbox", "dfsph"), ("mailbox", "wcsph"), ("mailbox", "pbd"),
+                                              ("nccl", "dfsph"), ("nccl", "wcsph"), ("torch", "dfsph")])
 def test_slabs_match_single_gpu_nccl(built, solver, transport):
     """One rank per GPU over NVLink: the native exchanges of csrc/sphk_mg.cu (peer-memory mailbox halos / NCCL halos)
     and the torch.distributed path must all reproduce the single-GPU result."""
