@@ -134,3 +134,38 @@ def test_choose_cuts_balances():
         cuts = slabs.choose_cuts(plane, 100, world)
         counts = [int(((plane >= a) & (plane < b)).sum()) for a, b in zip(cuts, cuts[1:])]
         assert sum(counts) == plane.size and max(counts) <= 1.25 * plane.size / world
+
+
+def test_plane_ranges_thin_slabs():
+    """plane_ranges for slabs of one, two and many planes: owned range, the (at most two) candidate planes per side,
+    first / last plane and ghost ranges stay consistent and never reach outside the owned range."""
+    import pkgload
+    pkgload.load()
+    from cpp_fluid_particles_b200.slabs import plane_ranges
+    rng = np.random.default_rng(7)
+    for w in (1, 2, 3, 9):
+        counts = rng.integers(0, 50, w + 2)                       # particles per local plane 0..w+1
+        off = np.concatenate([[0], np.cumsum(counts)])            # plane start offsets, off[w+2] = total
+        b = (off[0], off[1], off[min(2, w + 2)], off[min(3, w + 2)], off[max(w - 1, 0)], off[w], off[w + 1], off[w + 2])
+        r = plane_ranges(tuple(int(x) for x in b), w)
+        own = (int(off[1]), int(off[w + 1]))
+        assert r["own"] == own and r["ghost_l"] == (0, int(off[1])) and r["ghost_r"] == (int(off[w + 1]), int(off[w + 2]))
+        assert r["first"] == (int(off[1]), int(off[2])) and r["last"] == (int(off[w]), int(off[w + 1]))
+        for key in ("to_left", "to_right", "first", "last"):
+            lo, hi = r[key]
+            assert own[0] <= lo <= hi <= own[1], (w, key, r[key], own)
+        # candidates = the two outermost owned planes per side (all owned planes when the slab is thinner)
+        assert r["to_left"] == (own[0], int(off[min(3, w + 1)]))
+        assert r["to_right"] == (int(off[max(w - 1, 1)]), own[1])
+
+
+def test_choose_cuts_degenerate():
+    import pkgload
+    pkgload.load()
+    from cpp_fluid_particles_b200 import slabs
+    # every particle in one plane, more ranks than occupied planes: still strictly increasing cuts covering the grid
+    plane = np.full(1000, 5)
+    for world in (2, 3, 8):
+        cuts = slabs.choose_cuts(plane, 12, world)
+        assert cuts[0] == 0 and cuts[-1] == 12 and len(cuts) == world + 1
+        assert all(b > a for a, b in zip(cuts, cuts[1:]))
