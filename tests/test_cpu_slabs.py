@@ -169,3 +169,182 @@ def test_choose_cuts_degenerate():
         cuts = slabs.choose_cuts(plane, 12, world)
         assert cuts[0] == 0 and cuts[-1] == 12 and len(cuts) == world + 1
         assert all(b > a for a, b in zip(cuts, cuts[1:]))
+
+
+# ---- the NATIVE begin_step (SlabSystem._begin_step_native over csrc/sphk_mg.cu) with the C entry points replaced by
+# ---- gloo / numpy stand-ins: same host logic as on the GPUs (assembly straight into the scratch twins, swap, counts
+# ---- agreed one step ahead, ordering-contract check, halo ranges), no GPU, no library calls -------------------------
+def _native_worker(rank, world, port, steps, q):
+    import ctypes as C
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import pkgload
+    pkgload.load()
+    from cpp_fluid_particles_b200 import slabs
+    rng = np.random.default_rng(321)
+    n = 5000
+    pos = np.stack([rng.uniform(0.6, CX - 0.6, n), rng.uniform(0, CY, n), rng.uniform(0, CZ, n)], 1).astype(np.float32)
+    plane = pos[:, 0].astype(np.int64)
+    cuts = slabs.choose_cuts(plane, CX, world)
+    x0, x1 = cuts[rank], cuts[rank + 1]
+    w = x1 - x0
+    cap = n
+    left = rank - 1 if rank > 0 else None
+    right = rank + 1 if rank < world - 1 else None
+
+    def fview(ptr, count):          # float32 view of raw memory (what the C side would see)
+        return torch.from_numpy(np.ctypeslib.as_array((C.c_float * max(count, 1)).from_address(ptr))[:count])
+
+    def val(x):
+        return x.value if hasattr(x, "value") else x
+
+    def p2p(sends, recvs):
+        ops = [dist.P2POp(dist.isend, t, p) for t, p in sends] + [dist.P2POp(dist.irecv, t, p) for t, p in recvs]
+        if ops:
+            for wk in dist.batch_isend_irecv(ops):
+                wk.wait()
+
+    class FakeLib:                  # the sphk_* / sphk_mg_* calls _begin_step_native and _halo make
+        def sphk_mg_exchange_ints(self, mg, tl, tr, fl, fr, k):
+            k = val(k)
+            sends, recvs, bufs = [], [], {}
+            for side, peer, out in ((0, left, tl), (1, right, tr)):
+                if peer is not None:
+                    sends.append((torch.tensor(list(out)[:k], dtype=torch.int32), peer))
+                    bufs[side] = torch.zeros(k, dtype=torch.int32)
+                    recvs.append((bufs[side], peer))
+            p2p(sends, recvs)
+            for side, arr in ((0, fl), (1, fr)):
+                for i in range(k):
+                    arr[i] = int(bufs[side][i]) if side in bufs else 0
+            return 0
+
+        def sphk_mg_exchange_slices(self, mg, k, src, dst, widths, sl, sr, rl, rr):
+            sends, recvs = [], []
+            for a in range(val(k)):
+                wd = widths[a]
+                for peer, (b, c), arr, lst in ((left, sl, src, sends), (right, sr, src, sends), (left, rl, dst, recvs), (right, rr, dst, recvs)):
+                    if peer is not None and c > 0:
+                        lst.append((fview(arr[a] + 4 * wd * b, wd * c), peer))
+            p2p(sends, recvs)
+            return 0
+
+        def sphk_mg_halo(self, mg, ctx, scene, what, ptr, width, r):
+            base, wd = val(ptr), val(width)
+            sends, recvs = [], []
+            for peer, sb, sc_, gb, gc in ((left, r[0], r[1], r[4], r[5]), (right, r[2], r[3], r[6], r[7])):
+                if peer is not None:
+                    if sc_ > 0:
+                        sends.append((fview(base + 4 * wd * sb, wd * sc_).clone(), peer))
+                    if gc > 0:
+                        recvs.append((fview(base + 4 * wd * gb, wd * gc), peer))
+            p2p(sends, recvs)
+            return 0
+
+        def sphk_copy(self, ctx, dst, src, nf):
+            fview(val(dst), val(nf)).copy_(fview(val(src), val(nf)).clone())
+            return 0
+
+        def sphk_mg_check(self, mg, err):
+            err._obj.value = 0
+            return 0
+
+        def sphk_set_active_range(self, ctx, b, c):
+            return 0
+
+    class Fluid:
+        pass
+
+    class FakeSlab:
+        _begin_step_native = slabs.SlabSystem._begin_step_native
+        _swap_carried = slabs.SlabSystem._swap_carried
+        _exchange_ints = slabs.SlabSystem._exchange_ints
+        _carried = slabs.SlabSystem._carried
+        _bounds = slabs.SlabSystem._bounds
+        _search_all = slabs.SlabSystem._search_all
+        _halo = slabs.SlabSystem._halo
+
+        def _s(self):
+            return None
+
+        def search_fluid(self):         # stand-in for sphk_neighbor_search: stable sort of pos / vel by local cell key
+            m = self.fluid.n
+            c = np.floor(self.fluid.pos[:m].numpy()).astype(np.int64)
+            lx = c[:, 0] - (x0 - 1)
+            ok_ = (lx >= 0) & (lx < w + 2) & (c[:, 1] >= 0) & (c[:, 1] < CY) & (c[:, 2] >= 0) & (c[:, 2] < CZ)
+            ncl = (w + 2) * CY * CZ
+            k = np.where(ok_, (lx * CY + c[:, 1]) * CZ + c[:, 2], ncl)
+            o = torch.from_numpy(np.argsort(k, kind="stable"))
+            self.fluid.pos[:m] = self.fluid.pos[:m][o]
+            self.fluid.vel[:m] = self.fluid.vel[:m][o]
+            self.perm = o                                               # the solver permutes its history array itself
+            self.cs_fluid[:] = torch.from_numpy(np.searchsorted(k[o.numpy()], np.arange(ncl + 1), side="left").astype(np.int32))
+
+    s = FakeSlab()
+    s.L, s.mg, s.ctx = FakeLib(), object(), None
+    s.rank, s.world, s.device, s.cap, s.w, s.plane_cells, s.solver = rank, world, torch.device("cpu"), cap, w, CY * CZ, "dfsph"
+    s.ex = type("Ex", (), {"left": left, "right": right})()
+    s.fluid = Fluid()
+    s.fluid.pos, s.fluid.vel, s.warm = torch.zeros((cap, 3)), torch.zeros((cap, 3)), torch.zeros(cap)
+    s.cs_fluid = torch.zeros((w + 2) * CY * CZ + 1, dtype=torch.int32)
+    s._ranges, s.use_list, s.comm_s, s.time_assembly, s._assembly_events, s._scene = None, False, 0.0, False, [], None
+    mine = (plane >= x0) & (plane < x1)
+    s.n_own = int(mine.sum())
+    s.fluid.pos[:s.n_own] = torch.from_numpy(pos[mine])
+    s.fluid.vel[:s.n_own, 0] = torch.from_numpy(np.nonzero(mine)[0].astype(np.float32))     # vel.x carries the particle id
+    ok = True
+    for step in range(steps):
+        if step > 0:                      # every rank moves the GLOBAL set identically (< 1 plane), its own particles accordingly
+            dx = rng.uniform(-0.45, 0.45, (n, 3)).astype(np.float32)
+            dx[:, 1:] *= 0.2
+            pos = pos + dx
+            pos[:, 0] = np.clip(pos[:, 0], 0.05, CX - 0.05)
+            pos[:, 1] = np.clip(pos[:, 1], 0.01, CY - 0.01); pos[:, 2] = np.clip(pos[:, 2], 0.01, CZ - 0.01)
+            a0, a1 = s._ranges["own"]
+            ids = s.fluid.vel[a0:a1, 0].numpy().astype(np.int64)
+            s.fluid.pos[a0:a1] = torch.from_numpy(pos[ids])
+        s._begin_step_native()
+        s.warm[:s.fluid.n] = s.warm[:s.fluid.n][s.perm]                  # what step_dfsph's sphk_permute does
+        r = s._ranges
+        (o0, o1), (g0, g1), (h0, h1) = r["own"], r["ghost_l"], r["ghost_r"]
+        ids = s.fluid.vel[:h1, 0].numpy().astype(np.int64)
+        gplane = np.floor(pos[:, 0]).astype(np.int64)
+        ok &= g0 == 0 and g1 == o0 and o1 == h0
+        ok &= set(ids[o0:o1].tolist()) == set(np.nonzero((gplane >= x0) & (gplane < x1))[0].tolist()) and len(set(ids[o0:o1].tolist())) == o1 - o0
+        ok &= set(ids[g0:g1].tolist()) == set(np.nonzero(gplane == x0 - 1)[0].tolist())
+        ok &= set(ids[h0:h1].tolist()) == set(np.nonzero(gplane == x1)[0].tolist())
+        ok &= bool(np.array_equal(s.fluid.pos[:h1].numpy(), pos[ids]))
+        # the history array travelled with its particle (owned range): warm = id of the previous step's owner write
+        if step > 0:
+            ok &= bool(np.array_equal(s.warm[o0:o1].numpy(), (3.0 * ids[o0:o1] + (step - 1)).astype(np.float32)))
+        s.warm[o0:o1] = torch.from_numpy((3.0 * ids[o0:o1] + step).astype(np.float32))
+        # one halo of a scalar and one of a float3 array: ghosts must receive their owners' values, in sorted order
+        f = torch.zeros(cap)
+        f[o0:o1] = torch.from_numpy((2.0 * ids[o0:o1] + step).astype(np.float32))
+        s._halo(2, f)
+        ok &= bool(np.array_equal(f[:h1].numpy(), (2.0 * ids + step).astype(np.float32)))
+        g3 = torch.zeros((cap, 3))
+        g3[o0:o1] = s.fluid.pos[o0:o1] * 2.0
+        s._halo(0, g3)
+        ok &= bool(np.array_equal(g3[:h1].numpy(), pos[ids] * np.float32(2.0)))
+    allok = [None] * world
+    dist.all_gather_object(allok, bool(ok))
+    if rank == 0:
+        q.put(all(allok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_native_begin_step_host_logic_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_native_worker, args=(r, world, port, 6, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
