@@ -39,6 +39,10 @@ HM_FN int3 operator*(int s, int3 a) { return make_int3(s * a.x, s * a.y, s * a.z
 HM_FN int3 operator*(int3 a, int s) { return make_int3(a.x * s, a.y * s, a.z * s); }
 
 // ---- geometry -----------------------------------------------------------------------------
+#ifndef __CUDACC__
+// host-only parse of the reference HEADERS by g++ (tests/api_conformance.cpp); never executed
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+#endif
 HM_FN float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 HM_FN float length(float3 v) { return sqrtf(dot(v, v)); }
 HM_FN float3 normalize(float3 v) { return v * rsqrtf(dot(v, v)); }

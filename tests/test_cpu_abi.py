@@ -117,3 +117,27 @@ def test_headless_cli_scene_matches_benchmark_scenes_and_fails_loudly(pkg, built
         r = subprocess.run([cli, "--frames", "1"], capture_output=True, text=True, timeout=60)
         assert r.returncode == 3 and "no CPU path" in r.stderr
     assert subprocess.run([cli, "--solver", "nonsense"], capture_output=True, timeout=60).returncode == 2
+
+
+def test_class_api_conformance_compiles_against_both_header_sets():
+    """tests/api_conformance.cpp states the reference's public class API member by member (static_asserts).  It must
+    compile against this repository's headers and -- where the reference sources exist (this container, not the GPU
+    box) -- against the reference's own headers: same file, both engines."""
+    import shutil
+    import subprocess
+    src = os.path.join(ROOT, "tests", "api_conformance.cpp")
+    cxx = shutil.which("g++") or "/usr/bin/g++"
+    ours = [cxx, "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"),
+            "-I" + os.path.join(ROOT, "cpp-fluid-particles_b200", "host"), "-I/usr/local/cuda/include", src]
+    r = subprocess.run(ours, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = "/root/reference/src"
+    if os.path.isdir(ref):
+        theirs = [cxx, "-std=c++17", "-fsyntax-only", "-fpermissive", "-w", "-DSPH_APP_REFERENCE_ENGINE",
+                  "-I" + os.path.join(ROOT, "oracle", "ref_build"), "-I" + ref, "-I/usr/local/cuda/include", src]
+        r = subprocess.run(theirs, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-3000:]
+    # the assertions bite: a wrong signature is rejected
+    bad = open(src).read().replace("float (SPHSystem::*)()", "double (SPHSystem::*)()")
+    r = subprocess.run(ours[:-1] + ["-x", "c++", "-"], input=bad, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "float step()" in r.stderr
