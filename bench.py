@@ -363,6 +363,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dfsph", choices=["dfsph", "wcsph", "pbd"])
     ap.add_argument("--scene", default=None, help="override the scene (mini, config0, 200k, 2m, ...)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): 2M fluid particles per GPU, N=8 is BASELINE configs[4]; "
+                         "strong: the same scene (--scene, default 2m) split over N GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     import pkgload

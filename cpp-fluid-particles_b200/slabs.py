@@ -673,7 +673,8 @@ def bench_main(args, pkg) -> dict | None:
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     solver = args.workload
-    scene_name = args.scene or B.SCENE_OF_N[world]
+    strong = getattr(args, "scaling", "weak") == "strong"
+    scene_name = args.scene or ("2m" if strong else B.SCENE_OF_N[world])
     sc = pkg.scene.benchmark_scene(scene_name, solver)
     n = sc.fluid.shape[0]
     # a rank that dies must take the job down at once (its neighbours would wait for it inside a collective), and a job
@@ -684,7 +685,10 @@ def bench_main(args, pkg) -> dict | None:
     dog.daemon = True
     dog.start()
     try:
-        return _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name)
+        out = _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name)
+        if out is not None and strong:
+            out["scaling"] = "strong"
+        return out
     except BaseException:
         import traceback
         traceback.print_exc()
