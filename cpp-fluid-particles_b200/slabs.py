@@ -729,11 +729,20 @@ def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
     # ---- e2e: every step takes this rank's owned particles from pinned HOST buffers and returns them there ------------
     # (pos + vel in, pos + vel + density out; copies on the compute stream, inside the timed region)
     e2e = None
-    try:
+    hpos = hvel = hden = None
+    try:                                                   # the only rank-specific failure: pinned host memory
         cap = s.cap
         hpos = torch.empty((cap, 3), dtype=torch.float32, pin_memory=True)
         hvel = torch.empty((cap, 3), dtype=torch.float32, pin_memory=True)
         hden = torch.empty(cap, dtype=torch.float32, pin_memory=True)
+    except Exception as exc:
+        print(f"[bench] rank {rank}: no pinned buffers for the e2e leg: {exc}", file=sys.stderr, flush=True)
+        hpos = None
+    agree = torch.tensor([0.0 if hpos is None else 1.0], dtype=torch.float64, device=s.device)
+    dist.all_reduce(agree, op=dist.ReduceOp.MIN)           # all ranks run the leg, or none (a lone rank would wait for ever)
+    try:
+        if agree.item() < 1.0:
+            raise RuntimeError("skipped: a rank could not allocate its pinned buffers")
 
         def down():
             a, b = s._ranges["own"]
