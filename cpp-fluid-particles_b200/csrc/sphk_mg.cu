@@ -47,9 +47,8 @@ struct NcclApi {
     bool ok = false;
 };
 
-NcclApi& nccl() {
-    static NcclApi api;
-    if (api.lib) return api;
+NcclApi load_nccl() {
+    NcclApi api;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
         api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -68,6 +67,11 @@ NcclApi& nccl() {
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
     api.ok = all;
+    return api;
+}
+
+NcclApi& nccl() {
+    static NcclApi api = load_nccl();       // resolved once (thread-safe initialisation)
     return api;
 }
 
@@ -299,14 +303,15 @@ extern "C" int sphk_mg_init(sphk_mg_comm** out, int rank, int world, const unsig
     if (cudaMalloc(&m->dInts, 4 * SPHK_MG_MAX_INTS * sizeof(int)) != cudaSuccess ||
         cudaMallocHost(&m->hInts, 4 * SPHK_MG_MAX_INTS * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&m->dDouble, 2 * sizeof(double)) != cudaSuccess) {
-        delete m;
+        cudaGetLastError();
+        sphk_mg_destroy(m);
         return SPHK_ERR_ALLOC;
     }
     if (mailbox_floats > 0) {
         m->capFloats = static_cast<size_t>(mailbox_floats);
         m->boxBytes = (sizeof(MailHeader) + (m->capFloats + 4) * sizeof(float) + 255) / 256 * 256;
         const size_t total = sizeof(MailInfo) + 4 * m->boxBytes + 256;
-        if (cudaMalloc(&m->mail, total) != cudaSuccess) { delete m; return SPHK_ERR_ALLOC; }
+        if (cudaMalloc(&m->mail, total) != cudaSuccess) { cudaGetLastError(); m->mail = nullptr; sphk_mg_destroy(m); return SPHK_ERR_ALLOC; }
         cudaMemset(m->mail, 0, total);
         MailInfo info;
         std::memset(&info, 0, sizeof(info));
