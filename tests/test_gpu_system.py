@@ -86,6 +86,39 @@ def test_class_layer_vs_reference_cuda_200k(pkg, built):
 
 
 @pytest.mark.parametrize("solver", SOLVERS)
+def test_class_layer_vs_reference_cuda_2m(pkg, built, solver):
+    """BASELINE.json configs[1-3] at their real size (2 097 152 fluid + 237 608 boundary particles): the C++ class
+    layer against the reference's own CUDA kernels -- constructor state (step 0, Q3) and one explicit step.
+    Bit-exact particle2cell / cellStart / sorted boundary; <= 1e-5 scale-relative on positions and densities, and
+    <= 1e-5 PER ELEMENT on the densities of interior particles (rho >= 0.9 rho0: no free-surface cancellation)."""
+    _gpu()
+    if not os.path.exists(LIBREF):
+        pytest.skip("oracle/_ref/libsphref.so not built")
+    from cpp_fluid_particles_b200 import capi
+    sc = pkg.scene.benchmark_scene("2m", solver)
+    a, b = capi.SphApp(sc), capi.SphApp(sc, LIBREF)
+    ob, rb = a.download_boundary(), b.download_boundary()
+    assert np.array_equal(ob["p2c"], rb["p2c"])
+    assert np.array_equal(bits(ob["pos"]), bits(rb["pos"]))
+    assert_close(ob["mass"], rb["mass"], what="2m boundary mass")
+    nc = sc.params.ncells
+    for k in range(2):
+        sa, sb = a.download(), b.download()
+        assert np.array_equal(sa["p2c"], sb["p2c"]), f"2m {solver} step {k}: particle2cell differs"
+        assert np.array_equal(cell_start_from_p2c(sa["p2c"], nc), cell_start_from_p2c(sb["p2c"], nc))
+        assert_close(sa["pos"], sb["pos"], what=f"2m {solver} step {k} pos")
+        assert_close(sa["density"], sb["density"], what=f"2m {solver} step {k} density")
+        if solver == "pbd" and k == 0:
+            assert np.array_equal(bits(sa["pos"]), bits(sb["pos"])), "sort permutation differs from the reference"
+        interior = sb["density"] >= 0.9 * sc.params.rho0
+        if interior.any():
+            d = np.abs(sa["density"][interior].astype(np.float64) - sb["density"][interior]) / sb["density"][interior]
+            assert d.max() <= 1e-5, f"2m {solver} step {k}: per-element interior density error {d.max():.2e}"
+        a.step(); b.step()
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
 def test_sorted_order_bit_exact_through_steps(pkg, built, solver):
     """The stable-sort permutation and cellStart stay identical to the reference while the fluid moves:
     particle2cell of step k is computed from positions that already differ by ~1e-7, so exact equality of
