@@ -25,6 +25,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <new>
 
 // ---- the NCCL entry points this file uses (nccl.h 2.27: ncclUniqueId is 128 opaque bytes, passed by value) -------
 namespace {
@@ -115,6 +116,9 @@ int nccl_rc(int r) {
     return SPHK_ERR_COMM;
 }
 #define SPHK_NCCL_TRY(expr) do { const int r_ = nccl_rc(expr); if (r_ != SPHK_OK) return r_; } while (0)
+// inside ncclGroupStart/ncclGroupEnd: an error must still close the group, or every later NCCL call of the process
+// would be appended to it
+#define SPHK_NCCL_TRY_IN_GROUP(expr) do { const int r_ = nccl_rc(expr); if (r_ != SPHK_OK) { nccl().GroupEnd(); return r_; } } while (0)
 
 inline size_t flags_offset(const sphk_mg_comm* m) { return sizeof(MailInfo) + 4 * m->boxBytes; }
 inline unsigned char* box_of(unsigned char* base, const sphk_mg_comm* m, int side, int parity) {
@@ -176,6 +180,10 @@ __global__ void __launch_bounds__(kHaloBlock) k_halo_mailbox(HaloArgs a) {
         float* dst = reinterpret_cast<float*>(h.peerBox + sizeof(MailHeader));
         const float* src = h.src;
         const int n = h.sendFloats;
+        if (n < 0) {                               // oversize slice (host-side capacity check failed): header only
+            if (tid == 0) { int* hdr = reinterpret_cast<int*>(h.peerBox); hdr[0] = -1; hdr[1] = 0; }
+            continue;
+        }
         // the slice starts at an arbitrary particle: peel to 16-byte alignment of the SOURCE, the mailbox payload is
         // written with the same phase (payload offset = source misalignment), so both sides move float4s
         const int lead = static_cast<int>((reinterpret_cast<uintptr_t>(src) >> 2) & 3);   // floats past a 16-byte boundary
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(kHaloBlock) k_halo_mailbox(HaloArgs a) {
         if (!ok) continue;
         const int* hdr = reinterpret_cast<const int*>(h.myBox);
         const int n = __ldcg(hdr), lead = __ldcg(hdr + 1);
-        if (n != h.ghostCount * a.width) {            // ordering contract violated: report, do not touch memory
+        if (n != h.ghostCount * a.width) {            // ordering contract violated (or -1: the sender's slice was oversize): report, do not touch memory
             if (tid == 0) atomicOr(&a.tail->error, 4u << s);
             continue;
         }
@@ -294,7 +302,8 @@ extern "C" int sphk_mg_init(sphk_mg_comm** out, int rank, int world, const unsig
     if (!n.ok) return SPHK_ERR_COMM;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SPHK_ERR_NO_DEVICE;
-    sphk_mg_comm* m = new sphk_mg_comm();
+    sphk_mg_comm* m = new (std::nothrow) sphk_mg_comm();
+    if (!m) return SPHK_ERR_ALLOC;
     m->rank = rank; m->world = world; m->stream = static_cast<cudaStream_t>(stream);
     NcclUid u;
     std::memcpy(u.internal, id, 128);
@@ -388,12 +397,12 @@ extern "C" int sphk_mg_exchange_ints(sphk_mg_comm* m, const int* to_left, const 
     SPHK_CUDA_TRY(cudaMemcpyAsync(m->dInts, m->hInts, 4 * K * sizeof(int), cudaMemcpyHostToDevice, m->stream));
     SPHK_NCCL_TRY(n.GroupStart());
     if (m->rank > 0) {
-        SPHK_NCCL_TRY(n.Send(m->dInts, count, kNcclInt32, m->rank - 1, m->comm, m->stream));
-        SPHK_NCCL_TRY(n.Recv(m->dInts + 2 * K, count, kNcclInt32, m->rank - 1, m->comm, m->stream));
+        SPHK_NCCL_TRY_IN_GROUP(n.Send(m->dInts, count, kNcclInt32, m->rank - 1, m->comm, m->stream));
+        SPHK_NCCL_TRY_IN_GROUP(n.Recv(m->dInts + 2 * K, count, kNcclInt32, m->rank - 1, m->comm, m->stream));
     }
     if (m->rank < m->world - 1) {
-        SPHK_NCCL_TRY(n.Send(m->dInts + K, count, kNcclInt32, m->rank + 1, m->comm, m->stream));
-        SPHK_NCCL_TRY(n.Recv(m->dInts + 3 * K, count, kNcclInt32, m->rank + 1, m->comm, m->stream));
+        SPHK_NCCL_TRY_IN_GROUP(n.Send(m->dInts + K, count, kNcclInt32, m->rank + 1, m->comm, m->stream));
+        SPHK_NCCL_TRY_IN_GROUP(n.Recv(m->dInts + 3 * K, count, kNcclInt32, m->rank + 1, m->comm, m->stream));
     }
     SPHK_NCCL_TRY(n.GroupEnd());
     SPHK_CUDA_TRY(cudaMemcpyAsync(m->hInts + 2 * K, m->dInts + 2 * K, 2 * K * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -426,21 +435,21 @@ extern "C" int sphk_mg_exchange_slices(sphk_mg_comm* m, int narrays, const float
         const size_t w = static_cast<size_t>(widths[a]);
         if (L && send_left[1] > 0) {
             if (!any) { SPHK_NCCL_TRY(n.GroupStart()); any = true; }
-            SPHK_NCCL_TRY(n.Send(send_arrays[a] + send_left[0] * w, send_left[1] * w, kNcclFloat32, m->rank - 1, m->comm, m->stream));
+            SPHK_NCCL_TRY_IN_GROUP(n.Send(send_arrays[a] + send_left[0] * w, send_left[1] * w, kNcclFloat32, m->rank - 1, m->comm, m->stream));
             m->bytesSent += static_cast<long long>(send_left[1] * w * 4); m->messages++;
         }
         if (L && recv_left[1] > 0) {
             if (!any) { SPHK_NCCL_TRY(n.GroupStart()); any = true; }
-            SPHK_NCCL_TRY(n.Recv(recv_arrays[a] + recv_left[0] * w, recv_left[1] * w, kNcclFloat32, m->rank - 1, m->comm, m->stream));
+            SPHK_NCCL_TRY_IN_GROUP(n.Recv(recv_arrays[a] + recv_left[0] * w, recv_left[1] * w, kNcclFloat32, m->rank - 1, m->comm, m->stream));
         }
         if (R && send_right[1] > 0) {
             if (!any) { SPHK_NCCL_TRY(n.GroupStart()); any = true; }
-            SPHK_NCCL_TRY(n.Send(send_arrays[a] + send_right[0] * w, send_right[1] * w, kNcclFloat32, m->rank + 1, m->comm, m->stream));
+            SPHK_NCCL_TRY_IN_GROUP(n.Send(send_arrays[a] + send_right[0] * w, send_right[1] * w, kNcclFloat32, m->rank + 1, m->comm, m->stream));
             m->bytesSent += static_cast<long long>(send_right[1] * w * 4); m->messages++;
         }
         if (R && recv_right[1] > 0) {
             if (!any) { SPHK_NCCL_TRY(n.GroupStart()); any = true; }
-            SPHK_NCCL_TRY(n.Recv(recv_arrays[a] + recv_right[0] * w, recv_right[1] * w, kNcclFloat32, m->rank + 1, m->comm, m->stream));
+            SPHK_NCCL_TRY_IN_GROUP(n.Recv(recv_arrays[a] + recv_right[0] * w, recv_right[1] * w, kNcclFloat32, m->rank + 1, m->comm, m->stream));
         }
     }
     if (any) SPHK_NCCL_TRY(n.GroupEnd());
@@ -474,9 +483,10 @@ extern "C" int sphk_mg_halo(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, i
     }
     // ---- mailbox transport ----
     if (!m->connected) return SPHK_ERR_STATE;
-    if (static_cast<size_t>(ranges[1]) * width > m->capFloats || static_cast<size_t>(ranges[3]) * width > m->capFloats ||
-        static_cast<size_t>(ranges[5]) * width > m->capFloats || static_cast<size_t>(ranges[7]) * width > m->capFloats)
-        return SPHK_ERR_CAPACITY;
+    // a slice that does not fit a mailbox: the message is still sent (header only, count -1) so that the neighbours'
+    // sequence numbers stay in step and they see a size mismatch at once instead of a 20 s timeout
+    const bool tooBig = static_cast<size_t>(ranges[1]) * width > m->capFloats || static_cast<size_t>(ranges[3]) * width > m->capFloats ||
+                        static_cast<size_t>(ranges[5]) * width > m->capFloats || static_cast<size_t>(ranges[7]) * width > m->capFloats;
     const unsigned long long seq = ++m->seq;
     const int parity = static_cast<int>(seq & 1);
     MailTail* tail = reinterpret_cast<MailTail*>(m->mail + flags_offset(m));
@@ -486,7 +496,7 @@ extern "C" int sphk_mg_halo(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, i
     if (L) {
         MailTail* ptail = reinterpret_cast<MailTail*>(m->peer[0] + flags_offset(m));
         a.side[0].src = array + static_cast<size_t>(ranges[0]) * width;
-        a.side[0].sendFloats = ranges[1] * width;
+        a.side[0].sendFloats = tooBig ? -1 : ranges[1] * width;
         a.side[0].peerBox = box_of(m->peer[0], m, 1, parity);
         a.side[0].peerFlag = &ptail->flag[1];
         a.side[0].myBox = box_of(m->mail, m, 0, parity);
@@ -496,7 +506,7 @@ extern "C" int sphk_mg_halo(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, i
     if (R) {
         MailTail* ptail = reinterpret_cast<MailTail*>(m->peer[1] + flags_offset(m));
         a.side[1].src = array + static_cast<size_t>(ranges[2]) * width;
-        a.side[1].sendFloats = ranges[3] * width;
+        a.side[1].sendFloats = tooBig ? -1 : ranges[3] * width;
         a.side[1].peerBox = box_of(m->peer[1], m, 0, parity);
         a.side[1].peerFlag = &ptail->flag[0];
         a.side[1].myBox = box_of(m->mail, m, 1, parity);
@@ -521,7 +531,7 @@ extern "C" int sphk_mg_halo(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, i
     c->launches++;
     if (what & 4) c->posDirty = true;
     SPHK_CUDA_TRY(cudaGetLastError());
-    return SPHK_OK;
+    return tooBig ? SPHK_ERR_CAPACITY : SPHK_OK;
 }
 
 /* Reads the mailbox error word (synchronises the stream): 0 = fine; bit 0/1: timed out waiting for the left/right

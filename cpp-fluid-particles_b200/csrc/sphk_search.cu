@@ -350,8 +350,10 @@ extern "C" int sphk_fill(sphk_ctx* c, float* array, int n, float value) {
     if (array == c->sTag) c->sTag = nullptr;
     k_fill<<<sphk_blocks(n), SPHK_BLOCK, 0, c->stream>>>(array, n, value);
     c->launches++;
-    // the fluid mass fill of SPHSystem.cu:73 happens after the first fluid search packed mass into the
-    // shadow: keep the shadow coherent when the filled array is a bound mass array
+    // A fill of an API mass array AFTER the search that packed it (the reference kernels read mass[] live) is not
+    // mirrored here: the next sphk_neighbor_search / sphk_refresh re-packs it.  SPHSystem's constructor fills the
+    // fluid mass before the fluid search that precedes its first sweep (SPHSystem.cu:73-76), so the class layer never
+    // needs the refresh.
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;
 }

@@ -352,6 +352,9 @@ void SPHSystem::neighborSearch(const std::shared_ptr<SPHParticles>& particles, D
     const sphk_particles p = particles->abi();
     const int which = (particles.get() == _boundaries.get()) ? 1 : 0;
     check(sphk_neighbor_search(_engine->ctx(), which, &p, cellStart.addr()), "sphk_neighbor_search");
+    // the fluid search re-packs the records from the API arrays: edits made behind the engine's back
+    // (Particles::advect, raw pointer writes) are absorbed here, no separate sphk_refresh is needed
+    if (which == 0) _engine->shadowsStale = false;
 }
 
 // SPHSystem.cu:129-158
@@ -360,9 +363,21 @@ bool SPHSystem::solverIsGraphSafe() const {
     return known && known->stepIsGraphSafe();
 }
 
+unsigned int SPHSystem::solverConfigEpoch() const {
+    const auto* known = dynamic_cast<const BasicSPHSolver*>(_solver.get());
+    return known ? known->configEpoch() : 0u;
+}
+
+void SPHSystem::dropStepGraph() {
+    if (!_graphExec) return;
+    sphk_synchronize(_engine->ctx());
+    cudaGraphExecDestroy(_graphExec);
+    _graphExec = nullptr;
+}
+
 void SPHSystem::setStepGraph(bool on) {
     _graphEnabled = on;
-    if (!on && _graphExec) { sphk_synchronize(_engine->ctx()); cudaGraphExecDestroy(_graphExec); _graphExec = nullptr; }
+    if (!on) dropStepGraph();
 }
 
 // SPHSystem.cu:129-158.  Small scenes are launch-bound (~45 kernels of a few microseconds per DFSPH step): once
@@ -373,7 +388,12 @@ float SPHSystem::step() {
     cudaStream_t st = _engine->stream();
     sphk_ctx* ctx = _engine->ctx();
     CUDA_CALL(cudaEventRecord(_evStart, st));
+    // a captured step replays a fixed kernel sequence: drop it when the solver's settings changed or it stopped being
+    // replayable.  (Particles moved behind the engine's back need nothing special: the replayed step begins with the
+    // fluid neighbour search, which re-packs the records from the API arrays.)
+    if (_graphExec && (_graphConfigEpoch != solverConfigEpoch() || !solverIsGraphSafe())) dropStepGraph();
     if (_graphExec) {
+        _engine->shadowsStale = false;
         CUDA_CALL(cudaGraphLaunch(_graphExec, st));
         sphk_add_launches(ctx, _graphLaunches);
         check(sphk_synchronize(ctx), "step");
@@ -399,6 +419,7 @@ float SPHSystem::step() {
             if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph && ok &&
                 cudaGraphInstantiate(&_graphExec, graph, 0) == cudaSuccess) {
                 _graphLaunches = sphk_launch_count(ctx) - launches0;
+                _graphConfigEpoch = solverConfigEpoch();
                 CUDA_CALL(cudaGraphLaunch(_graphExec, st));     // the captured step has not run yet: run it now
             } else {
                 cudaGetLastError();
@@ -410,7 +431,11 @@ float SPHSystem::step() {
                     _solver->step(_fluids, _boundaries, cellStartFluid, cellStartBoundary, _spaceSize, _cellSize,
                                   _sphCellLength, _sphSmoothingRadius, _dt, _sphRho0, _sphRhoBoundary, _sphStiff, _sphVisc,
                                   _sphG, _sphSurfaceTensionIntensity, _sphAirPressure);
-                } catch (...) {}
+                } catch (const char* s) {
+                    std::cout << s << "\n";
+                } catch (...) {
+                    std::cout << "Unknown Exception at " << __FILE__ << ": line " << __LINE__ << "\n";
+                }
             }
             if (graph) cudaGraphDestroy(graph);
         }

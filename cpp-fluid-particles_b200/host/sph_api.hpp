@@ -12,6 +12,7 @@
 #include <iostream>
 #include <memory>
 #include <type_traits>
+#include <typeinfo>
 #include <vector>
 
 #include "sphk.h"
@@ -164,9 +165,13 @@ class BasicSPHSolver : public BaseSolver {
 public:
     explicit BasicSPHSolver(int num) : bufferFloat3(num), bufferColorGrad(num) {}
     // addition: false = one kernel per reference launch site (the per-op C-ABI path); true (default) = fused sweeps
-    void setFusedSweeps(bool on) { fusedSweeps_ = on; }
-    // addition: true when step() enqueues the same kernel sequence every call and never synchronises the host
-    virtual bool stepIsGraphSafe() const { return true; }
+    void setFusedSweeps(bool on) { if (on != fusedSweeps_) ++configEpoch_; fusedSweeps_ = on; }
+    // addition: true when step() enqueues the same kernel sequence every call and never synchronises the host.
+    // Only the three shipped solver types can say so: a user-derived solver (the reference API allows subclassing
+    // BasicSPHSolver) has per-step host logic of its own, so it is never captured into a step graph.
+    virtual bool stepIsGraphSafe() const { return typeid(*this) == typeid(BasicSPHSolver); }
+    // addition: bumped whenever a setting that changes the kernel sequence is modified (invalidates a captured graph)
+    unsigned int configEpoch() const { return configEpoch_; }
     virtual ~BasicSPHSolver() noexcept {}
     virtual void step(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
                       const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
@@ -195,6 +200,7 @@ protected:
     void diffuseAndSurface(float rho0, float rhoB, float visc, float dt, float surfaceTensionIntensity, float airPressure,
                            bool surface, bool colorGradReady);
     bool fusedSweeps_ = true;
+    unsigned int configEpoch_ = 0;
     bool beginStep(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
                    const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float radius,
                    bool neighborList, int listSkinPermille);
@@ -329,9 +335,12 @@ private:
     // CUDA graph of one whole step (fixed-iteration solvers only: the kernel sequence is then the same every step)
     cudaGraphExec_t _graphExec = nullptr;
     long long _graphLaunches = 0;
+    unsigned int _graphConfigEpoch = 0;   // solver configEpoch() the graph was captured with
     int _plainSteps = 0;
     bool _graphEnabled = true;
     bool solverIsGraphSafe() const;
+    unsigned int solverConfigEpoch() const;
+    void dropStepGraph();
     void computeBoundaryMass();
     void neighborSearch(const std::shared_ptr<SPHParticles>& particles, DArray<int>& cellStart);
 };
