@@ -32,9 +32,11 @@ SPHK_FUNCTIONS = [
 SPH_APP_FUNCTIONS = [
     "sph_app_create", "sph_app_destroy", "sph_app_step", "sph_app_fluid_size", "sph_app_boundary_size",
     "sph_app_download_fluid", "sph_app_download_boundary", "sph_app_upload_fluid", "sph_app_engine",
+    "sph_app_submit", "sph_app_wait",
 ]
 
 OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_LANES_PER_PARTICLE, OPT_LIST_SKIN, OPT_SIMPLE_LIST_BUILD = 1, 2, 4, 5, 6
+OPT_SCHEDULE, OPT_GROUP, OPT_TILE = 7, 8, 9
 
 
 class SphkGrid(C.Structure):
@@ -176,6 +178,17 @@ class SphApp:
             return C.c_void_p(a.ctypes.data) if a is not None else None
         if self.L.sph_app_upload_fluid(self.h, p(pos), p(vel)):
             raise RuntimeError("sph_app_upload_fluid failed")
+
+    def submit(self, pos_in, vel_in, pos_out=None, vel_out=None, density_out=None):
+        """Pipelined host-buffer step (include/sph_app.h): numpy arrays over pinned host memory."""
+        def p(a):
+            return C.c_void_p(a.ctypes.data) if a is not None else None
+        if self.L.sph_app_submit(self.h, p(pos_in), p(vel_in), p(pos_out), p(vel_out), p(density_out)):
+            raise RuntimeError("sph_app_submit failed")
+
+    def wait(self):
+        if self.L.sph_app_wait(self.h):
+            raise RuntimeError("sph_app_wait failed")
 
     def close(self):
         if getattr(self, "h", None):

@@ -8,18 +8,24 @@
 #define SPHK_PI (3.14159265358979323846f)       // global.h:22
 #define SPHK_MAX_A (1000.0f)                    // global.h:26
 #define SPHK_BLOCK 128
+#define SPHK_TILE_CAP 1535                      // records of a tile's staged neighbour windows (+1 dummy slot = 24 KiB per half)
+#define SPHK_TILE_WINS 18                       // 9 (dx,dy) rows of the fluid set + 9 of the boundary set
 
-// One particle = one 32-byte sector: a neighbour costs ONE 256-bit gather (LDG.E.256) in every sweep.
-//   x y z   : position                              (rewritten by the neighbour search / advect / PBD apply)
-//   s       : the scalar the NEXT sweep reads from its neighbours: DFSPH stiffness kappa, PBD lambda,
-//             p/rho^2 (pressure force) or |colour gradient|^2 (surface tension); 0 for boundary particles
-//   vx vy vz: velocity (0 for boundary particles)
-//   m       : mass
-// Sweeps that need position + scalar gather only the first half (16 bytes); the mass of a fluid neighbour
-// is the uniform m0 when every fluid mass is equal (checked on the device at each neighbour search, always
-// true for the reference's scenes, SPHSystem.cu:73), else -- and for boundary neighbours -- it is read from
-// the second half.
-struct __align__(32) Rec { float x, y, z, s, vx, vy, vz, m; };
+// Packed particle records, two 16-byte halves in two arrays (unified index: fluid j < capF, boundary capF + b,
+// one far-away zero-mass dummy at capF + capB used as list padding):
+//   A[j] = {x, y, z, s}     s = the scalar the NEXT sweep reads from its neighbours: DFSPH stiffness kappa, PBD lambda,
+//                           p/rho^2 (pressure force) or |colour gradient|^2 (surface tension).
+//                           BOUNDARY records carry their MASS in this slot (their scalar is always 0): a sweep that
+//                           gathers only A still has every neighbour's mass (fluid masses are uniform in the
+//                           reference's scenes, SPHSystem.cu:73; checked on the device at each search).
+//   B[j] = {vx, vy, vz, m}  velocity (0 for boundary particles) and mass
+// Sweeps that need position + scalar gather A only (one LDG.128 / one 16-byte slot of a staged tile); sweeps that
+// need the velocity gather A and B.  Two arrays (not one 32-byte struct) so that a tile's neighbour windows of A can
+// be staged into shared memory by contiguous bulk copies without dragging B along.
+struct Rec {
+    float4* a; float4* b;
+    __host__ __device__ __forceinline__ Rec operator+(long long i) const { return Rec{a + i, b + i}; }
+};
 
 // per-launch constants of the smoothing kernels (CUDAFunctions.cuh:23-54,82-98), evaluated once on the host
 struct KConst {
@@ -45,7 +51,7 @@ struct sphk_ctx {
     int *keys = nullptr, *keysSorted = nullptr, *idx = nullptr, *idxSorted = nullptr;
     void* cubTemp = nullptr; size_t cubTempBytes = 0;
     float4 *snapA = nullptr, *snapB = nullptr;   // [max(capF,capB)] snapshot / Jacobi temp
-    Rec* rec = nullptr;                          // [capF + capB] packed 32-byte particle records, sorted order
+    Rec rec = {nullptr, nullptr};                // [capF + capB + 1] packed particle records (two 16-byte halves), sorted order
     const void* sTag = nullptr;                  // which caller array rec[].s currently mirrors (nullptr: none)
     float* massRange = nullptr;                  // [2] device: min / max fluid mass of the last search (as float bits)
     float* tmpF = nullptr;                       // [3*capF] permute temp
@@ -62,6 +68,16 @@ struct sphk_ctx {
     float skin = 0.f;                // neighbour-list skin as a fraction of R (PBD: positions move inside a step)
     bool listHasSkin = false;        // the current list was built with a skin and displacement is being tracked
     unsigned int* dispMax = nullptr; // device: max squared displacement since the list build (float bits)
+    int tile = 0;                    // 1: tile lists -- 16-bit tile-local indices, neighbour windows staged in shared memory by
+                                     // bulk copies (k_build_tile / k_sweep_tile); 0: int32 lists gathered from global memory
+    int2* tileWin = nullptr;         // [tiles * 18] {first record, count} of the 9 fluid + 9 boundary windows of every tile
+    int group = 1;                   // list sweeps: particles per thread sharing ONE neighbour list (the union of their
+                                     // neighbours): 1 = a list per particle; 2 = consecutive pairs (2k, 2k+1) -- a gathered
+                                     // record serves both members, 27 % fewer gathers per particle at 1.26x the arithmetic
+    int schedule = 0;                // list sweeps: 0 = one block per 128-particle tile in launch order; 1 = persistent blocks,
+                                     // every SM works through its own contiguous chunk of tiles (L1 locality), stealing at the end
+    unsigned int* sched = nullptr;   // device: tile counter per SM [256] + finished-block counter (self-resetting)
+    int numSMs = 0;
     int lanesPerParticle = 1;        // list sweeps: 1 = thread per particle (default, faster on B200: profiles/), 4 = warp-cooperative quad
     unsigned long long searchEpoch = 0, listEpoch = ~0ull;
     int listBegin = 0, listEnd = 0;  // particle range the current list covers
@@ -73,7 +89,7 @@ struct sphk_ctx {
 };
 
 struct DevScene {
-    const Rec* rec;
+    Rec rec;
     const int* __restrict__ csF;
     const int* __restrict__ csB;
     const int* __restrict__ nbr;
@@ -83,6 +99,9 @@ struct DevScene {
     unsigned int dispLimit;
     float4* posBuild;                // positions at list build (skin lists)
     int nF, bOff, nbrStride, kmax;
+    const int2* tileWin;             // tile lists: the 18 windows of every tile (written by the list builder)
+    int dummy;                       // index of a record far away from everything with zero mass: list padding that
+                                     // contributes exactly 0 to every particle (group lists cannot pad with "self")
     int iBegin, iEnd;                // sweeps compute particles [iBegin, iEnd)
     int3 cs, org;
     float cellLength;
@@ -126,20 +145,18 @@ __device__ __forceinline__ int cell_index(int x, int y, int z, int3 cs) {
 }
 
 // ---- record access --------------------------------------------------------------------------------
-__device__ __forceinline__ float4 rec_lo(const Rec* r) { return *reinterpret_cast<const float4*>(r); }
-__device__ __forceinline__ float4 rec_hi(const Rec* r) { return *(reinterpret_cast<const float4*>(r) + 1); }
-// one 256-bit load (SASS LDG.E.256): both halves of a record in a single L1 request
-__device__ __forceinline__ void rec_full(const Rec* r, float4& lo, float4& hi) {
-    asm("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
-        : "l"(r));
+__device__ __forceinline__ float4 rec_lo(Rec r) { return *r.a; }
+__device__ __forceinline__ float4 rec_hi(Rec r) { return *r.b; }
+__device__ __forceinline__ void rec_full(Rec r, float4& lo, float4& hi) { lo = *r.a; hi = *r.b; }
+__device__ __forceinline__ void rec_store(Rec r, float4 lo, float4 hi) { *r.a = lo; *r.b = hi; }
+__device__ __forceinline__ void rec_set_pos(Rec r, float3 p) {
+    *reinterpret_cast<float2*>(&r.a->x) = make_float2(p.x, p.y); r.a->z = p.z;
 }
-__device__ __forceinline__ void rec_set_pos(Rec* r, float3 p) {
-    *reinterpret_cast<float2*>(&r->x) = make_float2(p.x, p.y); r->z = p.z;
+__device__ __forceinline__ void rec_set_vel(Rec r, float3 v) {
+    *reinterpret_cast<float2*>(&r.b->x) = make_float2(v.x, v.y); r.b->z = v.z;
 }
-__device__ __forceinline__ void rec_set_vel(Rec* r, float3 v) {
-    *reinterpret_cast<float2*>(&r->vx) = make_float2(v.x, v.y); r->vz = v.z;
-}
+__device__ __forceinline__ void rec_set_s(Rec r, float s) { r.a->w = s; }
+__device__ __forceinline__ float rec_m(Rec r) { return r.b->w; }
 
 // ---- smoothing kernels, CUDAFunctions.cuh:23-54,82-98 ------------------------------------------------
 // Same functions as the reference, arranged for the issue rate: constants folded per launch (KConst),

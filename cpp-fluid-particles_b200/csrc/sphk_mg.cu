@@ -158,7 +158,7 @@ struct HaloArgs {
     float* array;            // API array the ghost slices belong to (width floats per particle)
     int width;               // 1 or 3
     int what;                // sphk_push_range bit mask (0: array only)
-    Rec* rec;
+    Rec rec;
     const float4* posBuild;  // skin tracking (PBD position halos), or nullptr
     unsigned int* dispMax;
     unsigned long long timeoutNs;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kHaloBlock) k_halo_mailbox(HaloArgs a) {
             if (a.width == 1) {
                 const float v = __ldcg(pay + t);
                 a.array[i] = v;
-                if (a.what & 2) a.rec[i].s = v;
+                if (a.what & 2) rec_set_s(a.rec + i, v);
             } else {
                 const float3 v = f3(__ldcg(pay + 3 * t), __ldcg(pay + 3 * t + 1), __ldcg(pay + 3 * t + 2));
                 store3(a.array, i, v);

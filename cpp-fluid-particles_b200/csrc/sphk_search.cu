@@ -15,6 +15,7 @@
 // HBM-bound; algorithmic bytes per particle are listed in DESIGN.md.
 #include <cub/device/device_radix_sort.cuh>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include "sphk_internal.cuh"
 
@@ -38,7 +39,7 @@ k_hash_snapshot(const float* __restrict__ pos, const float* __restrict__ vel, in
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_gather(const int* __restrict__ idxSorted, const float4* __restrict__ snapPos,
          const float4* __restrict__ snapVel, const float* __restrict__ mass, int n,
-         float* __restrict__ pos, float* __restrict__ vel, Rec* __restrict__ rec, int isFluid,
+         float* __restrict__ pos, float* __restrict__ vel, Rec rec, int isFluid,
          unsigned int* __restrict__ massRange) {
     const int s = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     float m = 0.f;
@@ -46,7 +47,6 @@ k_gather(const int* __restrict__ idxSorted, const float4* __restrict__ snapPos,
         const int src = idxSorted[s];
         float4 p = snapPos[src];
         store3(pos, s, xyz(p));
-        p.w = 0.f;                          // rec.s
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (vel) {
             v = snapVel[src];
@@ -55,8 +55,8 @@ k_gather(const int* __restrict__ idxSorted, const float4* __restrict__ snapPos,
         }
         m = mass[s];                        // mass is NOT permuted by the reference (Q2): slot s keeps mass[s]
         v.w = m;
-        float4* out = reinterpret_cast<float4*>(rec + s);
-        out[0] = p; out[1] = v;
+        p.w = isFluid ? 0.f : m;            // A.w: neighbour scalar (fluid, none yet) / mass (boundary)
+        rec_store(rec + s, p, v);
     }
     if (isFluid) {                          // min / max fluid mass (non-negative floats order like their bits)
         float lo = (s < n) ? m : 3.0e38f, hi = (s < n) ? m : 0.f;
@@ -94,17 +94,15 @@ k_permute(const int* __restrict__ idxSorted, const float* __restrict__ src, floa
 
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_repack(const float* __restrict__ pos, const float* __restrict__ vel, const float* __restrict__ mass,
-         int n, Rec* __restrict__ rec, unsigned int* __restrict__ massRange) {
+         int n, Rec rec, int isFluid, unsigned int* __restrict__ massRange) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     float m = 0.f;
     if (i < n) {
         const float3 p = load3(pos, i);
         m = mass[i];
-        float4* out = reinterpret_cast<float4*>(rec + i);
-        out[0] = make_float4(p.x, p.y, p.z, 0.f);
         float4 v = make_float4(0.f, 0.f, 0.f, m);
         if (vel) { const float3 w = load3(vel, i); v = make_float4(w.x, w.y, w.z, m); }
-        out[1] = v;
+        rec_store(rec + i, make_float4(p.x, p.y, p.z, isFluid ? 0.f : m), v);
     }
     if (massRange) {
         float lo = (i < n) ? m : 3.0e38f, hi = (i < n) ? m : 0.f;
@@ -192,12 +190,28 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
     if (e == cudaSuccess) e = dalloc(&c->idxSorted, cap);
     if (e == cudaSuccess) e = dalloc(&c->snapA, cap);
     if (e == cudaSuccess) e = dalloc(&c->snapB, cap);
-    if (e == cudaSuccess) e = dalloc(&c->rec, tot);
+    if (e == cudaSuccess) e = dalloc(&c->rec.a, tot + 1);   // + the far-away zero-mass dummy record (list padding)
+    if (e == cudaSuccess) e = dalloc(&c->rec.b, tot + 1);
+    if (e == cudaSuccess) {
+        const float4 dummy = make_float4(1.0e6f, 1.0e6f, 1.0e6f, 0.f);
+        e = cudaMemcpy(c->rec.a + tot, &dummy, sizeof(float4), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = dalloc(&c->massRange, 2);
     if (e == cudaSuccess) e = dalloc(&c->dispMax, 1);
     if (e == cudaSuccess) e = dalloc(&c->tmpF, 3 * static_cast<size_t>(max_fluid));
     if (e == cudaSuccess) e = dalloc(&c->partial, 1024);
     if (e == cudaSuccess) e = dalloc(&c->cnt, static_cast<size_t>(max_fluid));
+    if (e == cudaSuccess) e = dalloc(&c->sched, 512);
+    if (e == cudaSuccess) e = dalloc(&c->tileWin, (static_cast<size_t>(max_fluid) / SPHK_BLOCK + 1) * SPHK_TILE_WINS);
+    if (e == cudaSuccess) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        e = cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, dev);
+        if (c->numSMs > 256) c->numSMs = 256;
+        if (const char* v = std::getenv("SPHK_SCHEDULE")) c->schedule = v[0] == '1' ? 1 : 0;
+        if (const char* v = std::getenv("SPHK_GROUP")) c->group = v[0] == '2' ? 2 : 1;
+        if (const char* v = std::getenv("SPHK_TILE")) c->tile = v[0] == '1' ? 1 : 0;
+    }
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&c->pinned), 64);
     if (e == cudaSuccess) {
         c->cubTempBytes = 0;
@@ -213,8 +227,8 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
 extern "C" void sphk_destroy(sphk_ctx* c) {
     if (!c) return;
     cudaFree(c->keys); cudaFree(c->keysSorted); cudaFree(c->idx); cudaFree(c->idxSorted);
-    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec); cudaFree(c->massRange); cudaFree(c->dispMax);
-    cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp);
+    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec.a); cudaFree(c->rec.b); cudaFree(c->massRange); cudaFree(c->dispMax);
+    cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp); cudaFree(c->sched); cudaFree(c->tileWin);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
 }
@@ -235,6 +249,17 @@ extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
         if (value < 0 || value > 1000) return SPHK_ERR_INVALID;
         if (value * 0.001f != c->skin) { c->skin = value * 0.001f; c->listEpoch = ~0ull; }
         return SPHK_OK;
+    case SPHK_OPT_TILE:
+        if (value != 0 && value != 1) return SPHK_ERR_INVALID;
+        if (value != c->tile) { c->tile = value; c->listEpoch = ~0ull; }
+        return SPHK_OK;
+    case SPHK_OPT_GROUP:
+        if (value != 1 && value != 2) return SPHK_ERR_INVALID;
+        if (value != c->group) { c->group = value; c->listEpoch = ~0ull; }
+        return SPHK_OK;
+    case SPHK_OPT_SCHEDULE:
+        if (value != 0 && value != 1) return SPHK_ERR_INVALID;
+        c->schedule = value; return SPHK_OK;
     case SPHK_OPT_LANES_PER_PARTICLE:
         if (value != 1 && value != 4) return SPHK_ERR_INVALID;
         c->lanesPerParticle = value; return SPHK_OK;
@@ -316,7 +341,7 @@ extern "C" int sphk_refresh(sphk_ctx* c, const sphk_scene* s) {
     if (!c || !s) return SPHK_ERR_INVALID;
     if (!c->fluidSearched || s->fluid.n != c->nF) return SPHK_ERR_STATE;
     k_init_mass_range<<<1, 1, 0, c->stream>>>(reinterpret_cast<unsigned int*>(c->massRange));
-    k_repack<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(s->fluid.pos, s->fluid.vel, s->fluid.mass, c->nF, c->rec,
+    k_repack<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(s->fluid.pos, s->fluid.vel, s->fluid.mass, c->nF, c->rec, 1,
                                                               reinterpret_cast<unsigned int*>(c->massRange));
     c->launches++;
     c->posDirty = true;
@@ -324,7 +349,7 @@ extern "C" int sphk_refresh(sphk_ctx* c, const sphk_scene* s) {
     c->sTag = nullptr;
     if (c->boundarySearched && s->boundary.pos && s->boundary.n == c->nB) {
         k_repack<<<sphk_blocks(c->nB), SPHK_BLOCK, 0, c->stream>>>(s->boundary.pos, nullptr, s->boundary.mass, c->nB,
-                                                                  c->rec + c->capF, nullptr);
+                                                                  c->rec + c->capF, 0, nullptr);
         c->launches++;
     }
     SPHK_CUDA_TRY(cudaGetLastError());

@@ -19,6 +19,7 @@
 // results agree with the reference kernels to ~1e-6 relative (tests/, <= 1e-5 required).
 // Compiled with -use_fast_math like the reference (Q10).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "sphk_internal.cuh"
 
@@ -47,7 +48,7 @@ struct OpDensity {
 // pressureForce_CUDA, BasicSPHSolver.cu:113-165.  rec.s = p / max(eps, rho^2), precomputed per particle
 // (identical value to the reference's per-pair expression); the particle's own value comes from its record.
 struct OpPressureForce {
-    Rec* rec; float* vel; float dt;
+    Rec rec; float* vel; float dt;
     static constexpr bool kFluidOnly = false, kHi = false;
     struct Acc { float3 a; float pri; template <class F> __device__ void sums(F f) { f(a.x); f(a.y); f(a.z); } };
     __device__ void begin(Acc& a, int, float4 lo, float4, const DevScene&) const { a.a = f3(0, 0, 0); a.pri = lo.w; }
@@ -98,7 +99,7 @@ struct OpColorGrad {
 
 // surfaceTensionAndAirPressure_CUDA, BasicSPHSolver.cu:332-370.  rec.s = dot(c, c) precomputed.
 struct OpSurface {
-    Rec* rec; float* vel; float dt, rho0, kappa, airP;
+    Rec rec; float* vel; float dt, rho0, kappa, airP;
     static constexpr bool kFluidOnly = true, kHi = false;
     struct Acc { float3 a; float cii, ratio; template <class F> __device__ void sums(F f) { f(a.x); f(a.y); f(a.z); } };
     __device__ void begin(Acc& a, int, float4 lo, float4, const DevScene&) const {
@@ -142,7 +143,7 @@ struct OpDensityAlpha {
 // (:74-116, kDensity=true; optionally with the warm-stiffness accumulate of :199-203 fused).
 // Writes the stiffness into rec.s as well: the following correct sweep gathers it with the positions.
 template <bool kDensity> struct OpDfsphError {
-    Rec* rec; const float* density; const float* alpha; float* error; float* stiff; float* warm;
+    Rec rec; const float* density; const float* alpha; float* error; float* stiff; float* warm;
     float dt, rho0;
     static constexpr bool kFluidOnly = false, kHi = true;
     struct Acc { float e; float3 vi; template <class F> __device__ void sums(F f) { f(e); } };
@@ -160,7 +161,7 @@ template <bool kDensity> struct OpDfsphError {
         error[i] = e;
         const float k = e * alpha[i];
         stiff[i] = k;
-        rec[i].s = k;
+        rec_set_s(rec + i, k);
         if (kDensity && warm) warm[i] += k;
     }
 };
@@ -168,7 +169,7 @@ template <bool kDensity> struct OpDfsphError {
 // correctDivergenceError_CUDA (DFSPHSolver.cu:308-329) / correctDensityError_CUDA (:118-158);
 // computeDeltaPos_CUDA (PBDSolver.cu:170-210) shares the pair term with lambda as the scalar.  Reads rec.s.
 template <int kMode /*0: vel += a, 1: vel += a/dt, 2: deltaPos = a/rho0*/> struct OpScalarGradient {
-    Rec* rec; float* vel; float* deltaPos; float dt_or_rho0;
+    Rec rec; float* vel; float* deltaPos; float dt_or_rho0;
     static constexpr bool kFluidOnly = false, kHi = false;
     struct Acc { float3 a; float ki; template <class F> __device__ void sums(F f) { f(a.x); f(a.y); f(a.z); } };
     __device__ void begin(Acc& a, int, float4 lo, float4, const DevScene&) const { a.a = f3(0, 0, 0); a.ki = lo.w; }
@@ -185,7 +186,7 @@ template <int kMode /*0: vel += a, 1: vel += a/dt, 2: deltaPos = a/rho0*/> struc
 
 // computeDensityLambda_CUDA, PBDSolver.cu:127-168 (rho0 passed through `bool`, Q4).  Writes lambda to rec.s.
 struct OpPbdLambda {
-    Rec* rec; float* density; float* lambda; float rho0, rho0AsBool, relaxation;
+    Rec rec; float* density; float* lambda; float rho0, rho0AsBool, relaxation;
     static constexpr bool kFluidOnly = false, kHi = false;
     struct Acc { float den, lam; float3 gs; template <class F> __device__ void sums(F f) { f(den); f(lam); f(gs.x); f(gs.y); f(gs.z); } };
     __device__ void begin(Acc& a, int, float4, float4, const DevScene&) const { a.den = 0.f; a.lam = 0.f; a.gs = f3(0, 0, 0); }
@@ -201,7 +202,7 @@ struct OpPbdLambda {
         float l = (a.den > rho0) ? (-(a.den / rho0 - 1.0f) / (dot3(a.gs, a.gs) + a.lam + SPHK_EPS)) : 0.0f;
         l *= relaxation;
         lambda[i] = l;
-        rec[i].s = l;
+        rec_set_s(rec + i, l);
     }
 };
 
@@ -300,15 +301,21 @@ struct OpViscositySurface {
 // =================================================================================================
 template <class Op>
 __device__ __forceinline__ void fetch(const DevScene& s, int j, float4& lo, float4& hi) {
-    if (Op::kHi) rec_full(s.rec + j, lo, hi);
-    else { lo = rec_lo(s.rec + j); hi = make_float4(0.f, 0.f, 0.f, 0.f); }
+    lo = rec_lo(s.rec + j);
+    if (Op::kHi) hi = rec_hi(s.rec + j);
+    else hi = make_float4(0.f, 0.f, 0.f, 0.f);
 }
-// mass of neighbour j: free when the second half was gathered; else the uniform fluid mass, or one extra
-// 4-byte load for boundary neighbours / non-uniform fluid masses
+// One candidate pair (i, j) with j's gathered halves.  Mass of the neighbour: the B half when it was gathered; else
+// the A half's fourth slot for a boundary neighbour (boundary records keep their mass there, their scalar is 0), the
+// uniform fluid mass for a fluid neighbour (one extra load when the fluid masses differ).
 template <class Op>
-__device__ __forceinline__ float mass_of(const DevScene& s, int j, bool isB, float4 hi, float m0) {
-    if (Op::kHi) return hi.w;
-    return (isB || m0 < 0.f) ? s.rec[j].m : m0;
+__device__ __forceinline__ void feed_pair(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float3 xi, int j, bool isB,
+                                          float4 lo, float4 hi, float m0, float3 d, float r2) {
+    float mj;
+    if (Op::kHi) mj = hi.w;
+    else mj = isB ? lo.w : (m0 < 0.f ? rec_m(s.rec + j) : m0);
+    lo.w = isB ? 0.0f : lo.w;
+    op.pair(acc, i, j, isB, d, r2, mj, lo, hi, s);
 }
 // uniform fluid mass of the last search, or -1 when the masses differ
 __device__ __forceinline__ float uniform_mass(const DevScene& s) {
@@ -342,7 +349,7 @@ __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, type
                 fetch<Op>(s, j, lo, hi);
                 const float3 d = xi - xyz(lo);
                 const float r2 = dot3(d, d);
-                if (r2 <= s.r2list) op.pair(acc, i, j, false, d, r2, mass_of<Op>(s, j, false, hi, m0), lo, hi, s);
+                if (r2 <= s.r2list) feed_pair(s, op, acc, i, xi, j, false, lo, hi, m0, d, r2);
             }
         }
         if (!Op::kFluidOnly) {
@@ -353,7 +360,7 @@ __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, type
                 fetch<Op>(s, j, lo, hi);
                 const float3 d = xi - xyz(lo);
                 const float r2 = dot3(d, d);
-                if (r2 <= s.r2list) op.pair(acc, i, j, true, d, r2, mass_of<Op>(s, j, true, hi, m0), lo, hi, s);
+                if (r2 <= s.r2list) feed_pair(s, op, acc, i, xi, j, true, lo, hi, m0, d, r2);
             }
         }
     }
@@ -377,13 +384,12 @@ __device__ __forceinline__ void list_pair(const DevScene& s, const Op& op, typen
     const bool isB = j >= s.bOff;
     if (Op::kFluidOnly && isB) return;
     const float3 d = xi - xyz(lo);
-    op.pair(acc, i, j, isB, d, dot3(d, d), mass_of<Op>(s, j, isB, hi, m0), lo, hi, s);
+    feed_pair(s, op, acc, i, xi, j, isB, lo, hi, m0, d, dot3(d, d));
 }
 
+// one particle's walk of its neighbour list (thread per particle)
 template <class Op>
-__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, const Op op) {
-    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= s.iEnd) return;
+__device__ __forceinline__ void sweep_list_particle(const DevScene& s, const Op& op, int i) {
     float4 lo, hi;
     rec_full(s.rec + i, lo, hi);
     const float3 xi = xyz(lo);
@@ -410,6 +416,426 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, con
         }
     } else {
         walk_cells(s, op, acc, i, lo, m0);  // more neighbours than the list keeps: exact fallback
+    }
+    op.end(acc, i, lo, hi, s);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, const Op op) {
+    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= s.iEnd) return;
+    sweep_list_particle(s, op, i);
+}
+
+// Persistent variant: tiles of SPHK_BLOCK consecutive particles are handed out per SM.  SM q owns the contiguous
+// run of tiles [q*T/S, (q+1)*T/S): the blocks resident on one SM work on adjacent tiles at the same time and on
+// the tiles of the adjacent cell columns right afterwards, so the neighbour records one tile pulled into L1 are hit
+// by the next ones (with launch-order scheduling the ~12 tiles resident on an SM are 148 tiles apart and every
+// record is fetched from L2 by ~10 different SMs; ncu: L1 hit rate 65 %, each missed sector costs a data-pipe
+// wavefront).  SMs that finish early take tiles from the following SMs' runs.  The counters reset themselves: the
+// last block to leave zeroes them for the next launch on the stream (no memset node, graph-replay safe).
+__device__ __forceinline__ unsigned int sm_id() { unsigned int r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+
+struct TileQueue {
+    unsigned int* ctr;      // [nsm] tiles handed out of each SM's run
+    unsigned int* done;     // blocks finished
+    int ntiles, nsm;
+    __device__ __forceinline__ int lo(int q) const { return static_cast<int>((static_cast<long long>(q) * ntiles) / nsm); }
+};
+
+// Next tile for this block (all threads call; the result is block-uniform), or -1 when every run is exhausted.
+// Own run first (one atomic by thread 0).  Once it is empty the block steals: all threads look at the other runs'
+// counters at once (one round trip instead of a sequential scan) and thread 0 takes a tile from the fullest one.
+__device__ __forceinline__ int next_tile(const TileQueue& tq, int sm, bool& stealing, int* sh /* [2] shared */) {
+    if (!stealing) {
+        if (threadIdx.x == 0) {
+            const int a = tq.lo(sm), len = tq.lo(sm + 1) - a;
+            const unsigned int c = atomicAdd(tq.ctr + sm, 1u);
+            sh[0] = c < static_cast<unsigned int>(len) ? a + static_cast<int>(c) : -1;
+        }
+        __syncthreads();
+        const int t = sh[0];
+        __syncthreads();
+        if (t >= 0) return t;
+        stealing = true;
+    }
+    for (;;) {
+        if (threadIdx.x == 0) sh[1] = 0;
+        __syncthreads();
+        for (int q = threadIdx.x; q < tq.nsm; q += SPHK_BLOCK) {
+            const int len = tq.lo(q + 1) - tq.lo(q);
+            const unsigned int c = *reinterpret_cast<volatile unsigned int*>(tq.ctr + q);
+            const int rem = c < static_cast<unsigned int>(len) ? len - static_cast<int>(c) : 0;
+            if (rem > 0) atomicMax(sh + 1, (rem << 9) | q);
+        }
+        __syncthreads();
+        const int best = sh[1];
+        if (best == 0) { __syncthreads(); return -1; }
+        if (threadIdx.x == 0) {
+            const int q = best & 511;
+            const int a = tq.lo(q), len = tq.lo(q + 1) - a;
+            const unsigned int c = atomicAdd(tq.ctr + q, 1u);
+            sh[0] = c < static_cast<unsigned int>(len) ? a + static_cast<int>(c) : -1;
+        }
+        __syncthreads();
+        const int t = sh[0];
+        __syncthreads();
+        if (t >= 0) return t;
+    }
+}
+__device__ __forceinline__ void leave_queue(const TileQueue& tq) {
+    __threadfence();
+    if (atomicAdd(tq.done, 1u) == gridDim.x - 1) {
+        for (int q = 0; q < tq.nsm; ++q) tq.ctr[q] = 0u;
+        *tq.done = 0u;
+        __threadfence();
+    }
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list_p(const DevScene s, const Op op, const TileQueue tq) {
+    __shared__ int sh[2];
+    const int sm = static_cast<int>(sm_id() % static_cast<unsigned int>(tq.nsm));
+    bool stealing = false;
+    for (;;) {
+        const int t = next_tile(tq, sm, stealing, sh);
+        if (t < 0) break;
+        const int i = s.iBegin + t * SPHK_BLOCK + threadIdx.x;
+        if (i < s.iEnd) sweep_list_particle(s, op, i);
+    }
+    if (threadIdx.x == 0) leave_queue(tq);
+}
+
+// Decomposition probes (tools/sweep_probe.py, SPHK_EXP=1|2|3; never used by the product path):
+//   1: gathers + list walk only (no pair arithmetic: the sum of one gathered word is kept alive)
+//   2: arithmetic only (every "neighbour" is the particle's own record, already in registers; the list is still read)
+//   3: gathers with ld.global.cg (bypass L1)
+template <class Op, int MODE>
+__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list_exp(const DevScene s, const Op op, float* sink) {
+    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= s.iEnd) return;
+    float4 lo, hi;
+    rec_full(s.rec + i, lo, hi);
+    const float3 xi = xyz(lo);
+    typename Op::Acc acc;
+    op.begin(acc, i, lo, hi, s);
+    const int n = s.cnt[i];
+    const float m0 = uniform_mass(s);
+    float keep = 0.f;
+    const int nb4 = (min(n, s.kmax) + 3) >> 2;
+    const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + i;
+    int4 jn = make_int4(i, i, i, i);
+    if (nb4 > 0) jn = __ldcs(row);
+    for (int b = 0; b < nb4; ++b) {
+        const int4 j4 = jn;
+        row += s.nbrStride;
+        if (b + 1 < nb4) jn = __ldcs(row);
+        float4 l0, h0, l1, h1, l2, h2, l3, h3;
+        if (MODE == 2) {
+            l0 = l1 = l2 = l3 = lo; h0 = h1 = h2 = h3 = hi;
+            l0.x += 1e-3f * (j4.x & 7); l1.y += 1e-3f * (j4.y & 7); l2.z += 1e-3f * (j4.z & 7); l3.x -= 1e-3f * (j4.w & 7);
+        } else if (MODE == 3) {
+            l0 = __ldcg(s.rec.a + j4.x); l1 = __ldcg(s.rec.a + j4.y); l2 = __ldcg(s.rec.a + j4.z); l3 = __ldcg(s.rec.a + j4.w);
+            h0 = h1 = h2 = h3 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (Op::kHi) { h0 = __ldcg(s.rec.b + j4.x); h1 = __ldcg(s.rec.b + j4.y); h2 = __ldcg(s.rec.b + j4.z); h3 = __ldcg(s.rec.b + j4.w); }
+        } else {
+            fetch<Op>(s, j4.x, l0, h0); fetch<Op>(s, j4.y, l1, h1); fetch<Op>(s, j4.z, l2, h2); fetch<Op>(s, j4.w, l3, h3);
+        }
+        if (MODE == 1) {
+            keep += l0.x + l1.y + l2.z + l3.w;
+            if (Op::kHi) keep += h0.x + h1.y + h2.z + h3.w;
+        } else {
+            list_pair(s, op, acc, i, xi, j4.x, l0, h0, m0);
+            list_pair(s, op, acc, i, xi, j4.y, l1, h1, m0);
+            list_pair(s, op, acc, i, xi, j4.z, l2, h2, m0);
+            list_pair(s, op, acc, i, xi, j4.w, l3, h3, m0);
+        }
+    }
+    if (MODE == 1) { if (keep == 123.456f) sink[0] = keep; }
+    else op.end(acc, i, lo, hi, s);
+}
+
+// Group variant: one thread computes G consecutive particles (G*k .. G*k+G-1) from ONE neighbour list, the union of
+// the members' neighbours in the cell walk's order.  Every gathered record is fed to all members: a candidate
+// outside a member's support contributes exactly 0 to it (W, grad W, the viscosity Laplacian and the surface-tension
+// gradient all select 0 beyond the support), so each member's sum is its own sum with zeros interleaved.  The point
+// is the L1 data pipe (ncu: 93 % busy, 35-49 % issue): consecutive particles share most of their neighbours
+// (lattice: 42 of 2x31), so gathers per particle drop by ~27 % at ~1.26x the arithmetic.
+// List padding is the far-away zero-mass dummy record (a member cannot be used: it is a real neighbour of its mates).
+template <class Op, int G>
+__device__ __forceinline__ void sweep_list_group(const DevScene& s, const Op& op, int k) {
+    int im[G]; bool on[G];
+    float4 lo[G], hi[G]; float3 xi[G];
+    typename Op::Acc acc[G];
+#pragma unroll
+    for (int m = 0; m < G; ++m) {
+        const int idx = k * G + m;
+        on[m] = idx >= s.iBegin && idx < s.iEnd;
+        im[m] = min(max(idx, s.iBegin), s.iEnd - 1);     // a masked member shadows a valid particle and writes nothing
+        rec_full(s.rec + im[m], lo[m], hi[m]);
+        xi[m] = xyz(lo[m]);
+        op.begin(acc[m], im[m], lo[m], hi[m], s);
+    }
+    int n = s.cnt[k];
+    const float m0 = uniform_mass(s);
+    if (s.dispMax && *s.dispMax > s.dispLimit) n = s.kmax + 1;     // skin exhausted: everybody walks the cells
+    if (n <= s.kmax) {
+        const int nb4 = (n + 3) >> 2;
+        const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + k;
+        int4 jn = make_int4(s.dummy, s.dummy, s.dummy, s.dummy);
+        if (nb4 > 0) jn = __ldcs(row);
+        for (int b = 0; b < nb4; ++b) {
+            const int4 j4 = jn;
+            row += s.nbrStride;
+            if (b + 1 < nb4) jn = __ldcs(row);
+            float4 l0, h0, l1, h1, l2, h2, l3, h3;
+            fetch<Op>(s, j4.x, l0, h0); fetch<Op>(s, j4.y, l1, h1); fetch<Op>(s, j4.z, l2, h2); fetch<Op>(s, j4.w, l3, h3);
+#pragma unroll
+            for (int m = 0; m < G; ++m) {
+                list_pair(s, op, acc[m], im[m], xi[m], j4.x, l0, h0, m0);
+                list_pair(s, op, acc[m], im[m], xi[m], j4.y, l1, h1, m0);
+                list_pair(s, op, acc[m], im[m], xi[m], j4.z, l2, h2, m0);
+                list_pair(s, op, acc[m], im[m], xi[m], j4.w, l3, h3, m0);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < G; ++m)
+            if (on[m]) walk_cells(s, op, acc[m], im[m], lo[m], m0);   // more neighbours than the list keeps: exact fallback
+    }
+#pragma unroll
+    for (int m = 0; m < G; ++m)
+        if (on[m]) op.end(acc[m], im[m], lo[m], hi[m], s);
+}
+
+template <class Op, int G>
+__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list_g(const DevScene s, const Op op) {
+    const int k = s.iBegin / G + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (k * G >= s.iEnd) return;
+    sweep_list_group<Op, G>(s, op, k);
+}
+
+// =================================================================================================
+// Tile lists: neighbour windows staged in shared memory (TMA bulk copies), 16-bit tile-local lists
+// =================================================================================================
+// A tile = SPHK_BLOCK consecutive particles of the sorted fluid set = one thread block.  Let [cA, cB] be the range of
+// cell indices its particles occupy.  z is the fastest cell dimension (CUDAFunctions.cuh:68), so for each of the nine
+// (dx,dy) rows every neighbour cell of every particle of the tile lies in the ONE contiguous cell range
+// [cA + off - 1, cB + off + 1], off = (dx*cs.y + dy)*cs.z, i.e. in one contiguous range of sorted records -- per set:
+// 9 fluid + 9 boundary windows, ~1300 records for a tile at the lattice density.  The list builder computes the windows
+// once per step (tileWin), every sweep copies them from the A (and, for velocity sweeps, B) record arrays into shared
+// memory with cp.async.bulk (one elected thread, completion on an mbarrier) while the threads load their own records,
+// and then walks per-particle lists of 16-bit slots of the staged arrays.  What this buys over gathering from global
+// memory (measured, profiles/r02): no L1 misses on the ~31 gathers per particle (each window record is fetched once per
+// tile as part of a full line instead of ~3.3 times as a lone 32-byte sector), and half the list traffic.
+// A tile whose windows exceed SPHK_TILE_CAP records, and particles outside the grid, fall back to the exact cell walk
+// (their count is stored as kmax + 1).
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return static_cast<unsigned int>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    unsigned int ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// thread 0: prefix sums of the window lengths; stages the windows when they fit.  Returns nothing; sPre[18] = total.
+__device__ __forceinline__ void tile_stage(const DevScene& s, const int2* sWin, int* sPre, float4* smA, float4* smB, bool wantB,
+                                           unsigned long long* bar) {
+    int t = 0;
+    for (int w = 0; w < SPHK_TILE_WINS; ++w) { sPre[w] = t; t += sWin[w].y; }
+    sPre[SPHK_TILE_WINS] = t;
+    if (t > SPHK_TILE_CAP) return;
+    smA[t] = make_float4(1.0e6f, 1.0e6f, 1.0e6f, 0.f);           // the dummy slot: list padding, contributes exactly 0
+    if (wantB) smB[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t == 0) return;
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, static_cast<unsigned int>(t) * 16u * (wantB ? 2u : 1u));
+    for (int w = 0; w < SPHK_TILE_WINS; ++w) {
+        const int len = sWin[w].y;
+        if (len <= 0) continue;
+        bulk_g2s(smA + sPre[w], s.rec.a + sWin[w].x, static_cast<unsigned int>(len) * 16u, bar);
+        if (wantB) bulk_g2s(smB + sPre[w], s.rec.b + sWin[w].x, static_cast<unsigned int>(len) * 16u, bar);
+    }
+}
+
+// ---- builder -----------------------------------------------------------------------------------------------------------
+// candidates [slot0, slot0 + count) of the staged A records against x; hits appended as 16-bit slots (two-phase, like
+// build_range: branch-free tests -> bit mask -> walk the set bits)
+__device__ __forceinline__ void build_range_tile(const float4* smA, int slot0, int count, float3 xi, float r2list, int selfSlot, int kmax,
+                                                 int& n, unsigned short*& wp, long long jump) {
+    for (int k0 = 0; k0 < count; k0 += 32) {
+        const int len = min(32, count - k0);
+        const float4* base = smA + slot0 + k0;
+        unsigned int mask = 0u;
+#pragma unroll 4
+        for (int k = 0; k < len; ++k) {
+            const float3 d = xi - xyz(base[k]);
+            mask |= (dot3(d, d) <= r2list ? 1u : 0u) << k;
+        }
+        const int self = selfSlot - (slot0 + k0);
+        if (self >= 0 && self < 32) mask &= ~(1u << self);
+        while (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (n < kmax) *wp = static_cast<unsigned short>(slot0 + k0 + k);
+            wp += ((n & 7) == 7) ? jump : 1;
+            ++n;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_build_tile(const DevScene s, unsigned short* __restrict__ nbr16, int* __restrict__ cnt, float4* __restrict__ posBuild,
+             int2* __restrict__ tileWin) {
+    extern __shared__ float4 smA[];                 // [SPHK_TILE_CAP + 1]
+    __shared__ unsigned long long bar;
+    __shared__ int sMin, sMax;
+    __shared__ int2 sWin[SPHK_TILE_WINS];
+    __shared__ int sPre[SPHK_TILE_WINS + 1];
+    const int tile = s.iBegin / SPHK_BLOCK + blockIdx.x;
+    const int i = tile * SPHK_BLOCK + threadIdx.x;
+    const bool have = i < s.nF;
+    const int ncells = s.cs.x * s.cs.y * s.cs.z;
+    if (threadIdx.x == 0) { sMin = 0x7fffffff; sMax = -1; }
+    __syncthreads();
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cx = 0, cy = 0, cz = 0, c = ncells;
+    if (have) {
+        lo = rec_lo(s.rec + i);
+        cx = cell_coord(lo.x, s.cellLength) - s.org.x; cy = cell_coord(lo.y, s.cellLength) - s.org.y; cz = cell_coord(lo.z, s.cellLength) - s.org.z;
+        c = cell_index(cx, cy, cz, s.cs);
+        if (c < ncells) { atomicMin(&sMin, c); atomicMax(&sMax, c); }
+    }
+    __syncthreads();
+    if (threadIdx.x < SPHK_TILE_WINS) {
+        int2 w = make_int2(0, 0);
+        if (sMax >= 0) {
+            const int r = threadIdx.x % 9;
+            const bool isB = threadIdx.x >= 9;
+            const long long off = (static_cast<long long>(r / 3 - 1) * s.cs.y + (r % 3 - 1)) * s.cs.z;
+            long long cl = sMin + off - 1, ch = sMax + off + 1;
+            if (cl < 0) cl = 0;
+            if (ch > ncells - 1) ch = ncells - 1;
+            if (cl <= ch) {
+                const int* cs = isB ? s.csB : s.csF;
+                const int a = cs[cl], b = cs[ch + 1];
+                w = make_int2(a + (isB ? s.bOff : 0), b - a);
+            }
+        }
+        sWin[threadIdx.x] = w;
+        tileWin[static_cast<size_t>(tile) * SPHK_TILE_WINS + threadIdx.x] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) tile_stage(s, sWin, sPre, smA, nullptr, false, &bar);
+    __syncthreads();
+    const int T = sPre[SPHK_TILE_WINS];
+    const bool staged = T <= SPHK_TILE_CAP;
+    if (staged && T > 0) mbar_wait(&bar, 0);        // every thread: the block must not retire with bulk copies in flight
+    if (!have || i < s.iBegin || i >= s.iEnd) return;
+    if (posBuild) posBuild[i] = lo;
+    if (!staged || c >= ncells) { cnt[i] = s.kmax + 1; return; }      // this particle walks the cells (exact fallback)
+    const float3 xi = xyz(lo);
+    const int zlo = max(cz - 1, 0), zhi = min(cz + 1, s.cs.z - 1);
+    const int selfSlot = sPre[4] + (i - sWin[4].x);
+    int n = 0;
+    unsigned short* wp = nbr16 + static_cast<size_t>(i) * 8;                  // entry 0 of particle i
+    const long long jump = static_cast<long long>(s.nbrStride) * 8 - 7;        // from entry 7 of batch b to entry 0 of batch b+1
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+        if (x < 0 || x >= s.cs.x || y < 0 || y >= s.cs.y) continue;
+        const int c0 = (x * s.cs.y + y) * s.cs.z;
+        {
+            const int a = s.csF[c0 + zlo], b = s.csF[c0 + zhi + 1];
+            build_range_tile(smA, sPre[r] + (a - sWin[r].x), b - a, xi, s.r2list, selfSlot, s.kmax, n, wp, jump);
+        }
+        {
+            const int a = s.csB[c0 + zlo], b = s.csB[c0 + zhi + 1];
+            if (b > a) build_range_tile(smA, sPre[r + 9] + (a + s.bOff - sWin[r + 9].x), b - a, xi, s.r2list, -1, s.kmax, n, wp, jump);
+        }
+    }
+    cnt[i] = n;
+    for (int m = n; (m & 7) && m < s.kmax; ++m) { *wp = static_cast<unsigned short>(T); ++wp; }   // pad the open batch with the dummy slot
+}
+
+// ---- sweep ----------------------------------------------------------------------------------------------------------------
+template <class Op>
+__device__ __forceinline__ void tile_pair(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float3 xi, int slot, int preB,
+                                          const float4* smA, const float4* smB, float m0) {
+    const bool isB = slot >= preB;
+    if (Op::kFluidOnly && isB) return;
+    const float4 lo = smA[slot];
+    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (Op::kHi) hi = smB[slot];
+    const float3 d = xi - xyz(lo);
+    feed_pair(s, op, acc, i, xi, -1, isB, lo, hi, m0, d, dot3(d, d));
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_tile(const DevScene s, const Op op) {
+    extern __shared__ float4 sm[];                  // A[SPHK_TILE_CAP + 1], then B[SPHK_TILE_CAP + 1] for velocity sweeps
+    float4* smA = sm;
+    float4* smB = sm + (SPHK_TILE_CAP + 1);
+    __shared__ unsigned long long bar;
+    __shared__ int2 sWin[SPHK_TILE_WINS];
+    __shared__ int sPre[SPHK_TILE_WINS + 1];
+    const int tile = s.iBegin / SPHK_BLOCK + blockIdx.x;
+    const int i = tile * SPHK_BLOCK + threadIdx.x;
+    const bool on = i >= s.iBegin && i < s.iEnd;
+    if (threadIdx.x < SPHK_TILE_WINS) sWin[threadIdx.x] = s.tileWin[static_cast<size_t>(tile) * SPHK_TILE_WINS + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) tile_stage(s, sWin, sPre, smA, smB, Op::kHi, &bar);
+    __syncthreads();
+    const int T = sPre[SPHK_TILE_WINS];
+    if (!on) {                                      // (the block must not retire with bulk copies in flight)
+        if (T > 0 && T <= SPHK_TILE_CAP) mbar_wait(&bar, 0);
+        return;
+    }
+    // own data and the first list batch travel while the bulk copies are in flight
+    float4 lo, hi;
+    rec_full(s.rec + i, lo, hi);
+    const float3 xi = xyz(lo);
+    typename Op::Acc acc;
+    op.begin(acc, i, lo, hi, s);
+    int n = s.cnt[i];
+    const float m0 = uniform_mass(s);
+    if (s.dispMax && *s.dispMax > s.dispLimit) n = s.kmax + 1;     // skin exhausted: everybody walks the cells
+    if (!Op::kHi && m0 < 0.f) n = s.kmax + 1;                      // non-uniform fluid masses: a sweep that stages A only has no neighbour mass
+    if (n <= s.kmax && T <= SPHK_TILE_CAP) {
+        const int nb8 = (n + 7) >> 3;
+        const uint4* __restrict__ row = reinterpret_cast<const uint4*>(s.nbr) + i;
+        uint4 jn = make_uint4(0u, 0u, 0u, 0u);
+        if (nb8 > 0) jn = __ldcs(row);
+        if (T > 0) mbar_wait(&bar, 0);
+        const int preB = sPre[9];
+        for (int b = 0; b < nb8; ++b) {
+            const uint4 j8 = jn;
+            row += s.nbrStride;
+            if (b + 1 < nb8) jn = __ldcs(row);
+            tile_pair(s, op, acc, i, xi, static_cast<int>(j8.x & 0xffffu), preB, smA, smB, m0);
+            tile_pair(s, op, acc, i, xi, static_cast<int>(j8.x >> 16), preB, smA, smB, m0);
+            tile_pair(s, op, acc, i, xi, static_cast<int>(j8.y & 0xffffu), preB, smA, smB, m0);
+            tile_pair(s, op, acc, i, xi, static_cast<int>(j8.y >> 16), preB, smA, smB, m0);
+            tile_pair(s, op, acc, i, xi, static_cast<int>(j8.z & 0xffffu), preB, smA, smB, m0);
+            tile_pair(s, op, acc, i, xi, static_cast<int>(j8.z >> 16), preB, smA, smB, m0);
+            tile_pair(s, op, acc, i, xi, static_cast<int>(j8.w & 0xffffu), preB, smA, smB, m0);
+            tile_pair(s, op, acc, i, xi, static_cast<int>(j8.w >> 16), preB, smA, smB, m0);
+        }
+    } else {
+        if (T > 0 && T <= SPHK_TILE_CAP) mbar_wait(&bar, 0);
+        walk_cells(s, op, acc, i, lo, m0);          // exact fallback (global gathers)
     }
     op.end(acc, i, lo, hi, s);
 }
@@ -469,7 +895,7 @@ __device__ __forceinline__ void build_range(const DevScene& s, float3 xi, int i,
                                             long long jump) {
     for (int j0 = a; j0 < b; j0 += 32) {
         const int len = min(32, b - j0);
-        const Rec* base = s.rec + off + j0;
+        const Rec base = s.rec + off + j0;
         unsigned int mask = 0u;
 #pragma unroll 4
         for (int k = 0; k < len; ++k) {
@@ -516,9 +942,81 @@ k_build_list(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, flo
     if (posBuild) posBuild[i] = lo;
 }
 
+// Pair-list builder (SPHK_OPT_GROUP = 2): thread k builds the union list of particles 2k and 2k+1.
+// Common case -- both members in the same cell column: the 3-cell z-windows of both merge into ONE contiguous range
+// per (dx,dy) row, every candidate is tested against both members and kept if it lies in either support; the kept
+// order is the cell walk's order, so each member sees its own neighbours in the order of its own walk.
+// Rare case (the pair straddles two columns, or a member lies outside the grid): member 0's walk keeps its own
+// neighbours, member 1's walk keeps those not already kept (a neighbour of member 0 always lies in member 0's
+// 27 cells).  Same two-phase structure as k_build_list (branch-free tests -> bit mask -> walk the set bits).
+template <int kMode /*0: hit either member; 1: hit member 0; 2: hit member 1 and not member 0*/>
+__device__ __forceinline__ void build_range2(const DevScene& s, float3 x0, float3 x1, int a, int b, int off, int& n, int*& wp,
+                                             long long jump) {
+    for (int j0 = a; j0 < b; j0 += 32) {
+        const int len = min(32, b - j0);
+        const Rec base = s.rec + off + j0;
+        unsigned int mask = 0u;
+#pragma unroll 4
+        for (int k = 0; k < len; ++k) {
+            const float3 p = xyz(rec_lo(base + k));
+            const float3 d0 = x0 - p, d1 = x1 - p;
+            const bool h0 = dot3(d0, d0) <= s.r2list, h1 = dot3(d1, d1) <= s.r2list;
+            const bool hit = kMode == 0 ? (h0 || h1) : kMode == 1 ? h0 : (h1 && !h0);
+            mask |= (hit ? 1u : 0u) << k;
+        }
+        while (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (n < s.kmax) *wp = off + j0 + k;
+            wp += ((n & 3) == 3) ? jump : 1;
+            ++n;
+        }
+    }
+}
+
+template <int kMode>
+__device__ __forceinline__ void build_walk2(const DevScene& s, float3 x0, float3 x1, int cx, int cy, int zlo, int zhi, int& n, int*& wp,
+                                            long long jump) {
+    if (zlo > zhi) return;
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+        if (x < 0 || x >= s.cs.x || y < 0 || y >= s.cs.y) continue;
+        const int c0 = (x * s.cs.y + y) * s.cs.z;
+        build_range2<kMode>(s, x0, x1, s.csF[c0 + zlo], s.csF[c0 + zhi + 1], 0, n, wp, jump);
+        build_range2<kMode>(s, x0, x1, s.csB[c0 + zlo], s.csB[c0 + zhi + 1], s.bOff, n, wp, jump);
+    }
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_build_list2(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, float4* __restrict__ posBuild) {
+    const int k = s.iBegin / 2 + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    const int i0 = 2 * k;
+    if (i0 >= s.iEnd) return;
+    const int i1 = min(i0 + 1, s.nF - 1);           // odd particle count: the last pair is (i, i)
+    const float4 lo0 = rec_lo(s.rec + i0), lo1 = rec_lo(s.rec + i1);
+    const float3 x0 = xyz(lo0), x1 = xyz(lo1);
+    const int cx0 = cell_coord(lo0.x, s.cellLength) - s.org.x, cy0 = cell_coord(lo0.y, s.cellLength) - s.org.y,
+              cz0 = cell_coord(lo0.z, s.cellLength) - s.org.z;
+    const int cx1 = cell_coord(lo1.x, s.cellLength) - s.org.x, cy1 = cell_coord(lo1.y, s.cellLength) - s.org.y,
+              cz1 = cell_coord(lo1.z, s.cellLength) - s.org.z;
+    int n = 0;
+    int* wp = nbr + static_cast<size_t>(k) * 4;
+    const long long jump = static_cast<long long>(s.nbrStride) * 4 - 3;
+    if (cx0 == cx1 && cy0 == cy1) {
+        build_walk2<0>(s, x0, x1, cx0, cy0, max(min(cz0, cz1) - 1, 0), min(max(cz0, cz1) + 1, s.cs.z - 1), n, wp, jump);
+    } else {
+        build_walk2<1>(s, x0, x1, cx0, cy0, max(cz0 - 1, 0), min(cz0 + 1, s.cs.z - 1), n, wp, jump);
+        build_walk2<2>(s, x0, x1, cx1, cy1, max(cz1 - 1, 0), min(cz1 + 1, s.cs.z - 1), n, wp, jump);
+    }
+    cnt[k] = n;
+    for (int m = n; (m & 3) && m < s.kmax; ++m) { *wp = s.dummy; ++wp; }     // pad the open batch with the dummy record
+    if (posBuild) { posBuild[i0] = lo0; if (i1 != i0) posBuild[i1] = lo1; }
+}
+
 // computeBoundaryMass_CUDA, SPHSystem.cu:79-105: boundary particles against the boundary set only
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_boundary_mass(Rec* __restrict__ recB, float* __restrict__ mass, int n, const int* __restrict__ csB, int3 cs, int3 org,
+k_boundary_mass(Rec recB, float* __restrict__ mass, int n, const int* __restrict__ csB, int3 cs, int3 org,
                 float cellLength, float rhoB, KConst k) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= n) return;
@@ -537,13 +1035,14 @@ k_boundary_mass(Rec* __restrict__ recB, float* __restrict__ mass, int n, const i
     }
     mass[i] = rhoB / fmaxf(SPHK_EPS, sum);
 }
-__global__ void __launch_bounds__(SPHK_BLOCK) k_set_mass(Rec* __restrict__ rec, const float* __restrict__ mass, int n) {
+// boundary records: the mass lives in both halves (A.w for sweeps that gather A only, B.w for the others)
+__global__ void __launch_bounds__(SPHK_BLOCK) k_set_mass(Rec rec, const float* __restrict__ mass, int n) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i < n) rec[i].m = mass[i];
+    if (i < n) { const float m = mass[i]; rec.a[i].w = m; rec.b[i].w = m; }
 }
 
 // ---- element-wise kernels -------------------------------------------------------------------------
-__global__ void __launch_bounds__(SPHK_BLOCK) k_gravity(Rec* __restrict__ rec, float* __restrict__ vel, int n, float3 dv) {
+__global__ void __launch_bounds__(SPHK_BLOCK) k_gravity(Rec rec, float* __restrict__ vel, int n, float3 dv) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= n) return;
     const float4 hi = rec_hi(rec + i);
@@ -562,19 +1061,19 @@ k_pressure(const float* __restrict__ density, float* __restrict__ pressure, int 
 }
 // rec.s producers for the sweeps whose neighbour scalar is not written by the preceding sweep
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_s_prho(const float* __restrict__ density, const float* __restrict__ pressure, Rec* __restrict__ rec, int n) {
+k_s_prho(const float* __restrict__ density, const float* __restrict__ pressure, Rec rec, int n) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i < n) rec[i].s = pressure[i] / fmaxf(SPHK_EPS, density[i] * density[i]);
+    if (i < n) rec_set_s(rec + i, pressure[i] / fmaxf(SPHK_EPS, density[i] * density[i]));
 }
-__global__ void __launch_bounds__(SPHK_BLOCK) k_s_cg2(const float* __restrict__ cg, Rec* __restrict__ rec, int n) {
+__global__ void __launch_bounds__(SPHK_BLOCK) k_s_cg2(const float* __restrict__ cg, Rec rec, int n) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= n) return;
     const float3 c = load3(cg, i);
-    rec[i].s = dot3(c, c);
+    rec_set_s(rec + i, dot3(c, c));
 }
-__global__ void __launch_bounds__(SPHK_BLOCK) k_s_copy(const float* __restrict__ a, Rec* __restrict__ rec, int n) {
+__global__ void __launch_bounds__(SPHK_BLOCK) k_s_copy(const float* __restrict__ a, Rec rec, int n) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i < n) rec[i].s = a[i];
+    if (i < n) rec_set_s(rec + i, a[i]);
 }
 
 // Particles::advect (Particles.cu:28-36) + enforceBoundary_CUDA(pos, vel) (BasicSPHSolver.cu:85-96)
@@ -583,20 +1082,19 @@ __device__ __forceinline__ void clamp_axis(float& p, float* v, float L) {
     if (p >= L * .99f) { p = L * .99f; if (v) *v = fminf(*v, 0.0f); }
 }
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_advect(Rec* __restrict__ rec, float* __restrict__ pos, float* __restrict__ vel, int n, float dt, float3 space) {
+k_advect(Rec rec, float* __restrict__ pos, float* __restrict__ vel, int n, float dt, float3 space) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= n) return;
     float4 p, v;
     rec_full(rec + i, p, v);
     p.x = p.x + dt * v.x; p.y = p.y + dt * v.y; p.z = p.z + dt * v.z;
     clamp_axis(p.x, &v.x, space.x); clamp_axis(p.y, &v.y, space.y); clamp_axis(p.z, &v.z, space.z);
-    float4* out = reinterpret_cast<float4*>(rec + i);
-    out[0] = p; out[1] = v;
+    rec_store(rec + i, p, v);
     store3(pos, i, xyz(p)); store3(vel, i, xyz(v));
 }
 // thrust::transform(pos += dpos) + enforceBoundary_CUDA(pos), PBDSolver.cu:212-223,247-253
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_apply_delta_pos(Rec* __restrict__ rec, float* __restrict__ pos, const float* __restrict__ dpos, int n, float3 space,
+k_apply_delta_pos(Rec rec, float* __restrict__ pos, const float* __restrict__ dpos, int n, float3 space,
                   const float4* __restrict__ posBuild, unsigned int* __restrict__ dispMax) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     float d2 = 0.f;
@@ -615,14 +1113,14 @@ k_apply_delta_pos(Rec* __restrict__ rec, float* __restrict__ pos, const float* _
 }
 // vel = (pos - posLast) / dt, PBDSolver.cu:55-60
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_vel_from_pos(Rec* __restrict__ rec, const float* __restrict__ posLast, float* __restrict__ vel, int n, float dt) {
+k_vel_from_pos(Rec rec, const float* __restrict__ posLast, float* __restrict__ vel, int n, float dt) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= n) return;
     const float3 v = (xyz(rec_lo(rec + i)) - load3(posLast, i)) / dt;
     rec_set_vel(rec + i, v); store3(vel, i, v);
 }
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_commit_vel(const float4* __restrict__ src, Rec* __restrict__ rec, float* __restrict__ vel, int begin, int end) {
+k_commit_vel(const float4* __restrict__ src, Rec rec, float* __restrict__ vel, int begin, int end) {
     const int i = begin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= end) return;
     const float3 v = xyz(src[i]);
@@ -671,7 +1169,13 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
     DevScene d;
     d.rec = c->rec; d.csF = s->cell_start_fluid; d.csB = s->cell_start_boundary;
     d.nbr = c->nbr; d.cnt = c->cnt; d.massRange = c->massRange;
-    d.nF = c->nF; d.bOff = c->capF; d.nbrStride = c->capF; d.kmax = c->kmax;
+    d.nF = c->nF; d.bOff = c->capF;
+    // pair lists: half as many lists, each up to twice as long (same storage)
+    d.nbrStride = c->group == 2 ? (c->capF + 1) / 2 : c->capF;
+    d.kmax = c->group == 2 ? 2 * c->kmax : c->kmax;
+    d.dummy = c->capF + c->capB;
+    d.tileWin = c->tileWin;
+    if (c->tile) { d.nbrStride = c->capF; d.kmax = c->kmax; }
     d.cs = c->cs; d.org = c->org; d.cellLength = c->cellLength;
     d.iBegin = c->actCount < 0 ? 0 : c->actBegin;
     d.iEnd = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
@@ -685,7 +1189,7 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
     // lists are built for the particles the sweeps will compute (the active range: ghosts of a slab rank need none)
     if (c->listEpoch == c->searchEpoch && d.iBegin >= c->listBegin && d.iEnd <= c->listEnd) return SPHK_OK;
     if (!c->nbr) {
-        const size_t bytes = sizeof(int) * static_cast<size_t>(c->kmax) * static_cast<size_t>(c->capF);
+        const size_t bytes = sizeof(int) * static_cast<size_t>(c->kmax) * (static_cast<size_t>(c->capF) + 2);
         if (cudaMalloc(reinterpret_cast<void**>(&c->nbr), bytes) != cudaSuccess) { cudaGetLastError(); return SPHK_ERR_ALLOC; }
     }
     DevScene b = d;
@@ -697,7 +1201,17 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
         b.r2list = rs * rs * (1.0f + 1e-5f);
         if (cudaMemsetAsync(c->dispMax, 0, sizeof(unsigned int), c->stream) != cudaSuccess) return SPHK_ERR_STATE;
     }
-    if (c->simpleBuild) {
+    if (c->tile) {
+        static bool attr = false;
+        const int smem = (SPHK_TILE_CAP + 1) * 16;
+        if (!attr) { cudaFuncSetAttribute(k_build_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+        const int tiles = (b.iEnd + SPHK_BLOCK - 1) / SPHK_BLOCK - b.iBegin / SPHK_BLOCK;
+        k_build_tile<<<tiles, SPHK_BLOCK, smem, c->stream>>>(b, reinterpret_cast<unsigned short*>(c->nbr), c->cnt,
+                                                              c->listHasSkin ? c->snapA : nullptr, c->tileWin);
+    } else if (c->group == 2) {
+        const int groups = (b.iEnd + 1) / 2 - b.iBegin / 2;
+        k_build_list2<<<sphk_blocks(groups), SPHK_BLOCK, 0, c->stream>>>(b, c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr);
+    } else if (c->simpleBuild) {
         OpBuildList op{c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr};
         k_sweep_cells<OpBuildList><<<sphk_blocks(b.iEnd - b.iBegin), SPHK_BLOCK, 0, c->stream>>>(b, op);
     } else {
@@ -724,7 +1238,33 @@ template <class Op> static int run_sweep(sphk_ctx* c, const sphk_scene* s, const
             d.dispMax = c->dispMax;
             memcpy(&d.dispLimit, &lim, sizeof(float));
         }
-        if (c->lanesPerParticle == 4) k_sweep_list4<Op><<<sphk_blocks(4 * (d.iEnd - d.iBegin)), SPHK_BLOCK, 0, c->stream>>>(d, op);
+        static const int expMode = [] { const char* v = std::getenv("SPHK_EXP"); return v ? atoi(v) : 0; }();
+        if (c->tile && expMode == 0) {
+            static bool attr = false;
+            const int smem = (SPHK_TILE_CAP + 1) * 16 * (Op::kHi ? 2 : 1);
+            if (!attr) { cudaFuncSetAttribute(k_sweep_tile<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+            const int tiles = (d.iEnd + SPHK_BLOCK - 1) / SPHK_BLOCK - d.iBegin / SPHK_BLOCK;
+            k_sweep_tile<Op><<<tiles, SPHK_BLOCK, smem, c->stream>>>(d, op);
+        }
+        else if (expMode == 1) k_sweep_list_exp<Op, 1><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op, c->partial);
+        else if (expMode == 2) k_sweep_list_exp<Op, 2><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op, c->partial);
+        else if (expMode == 3) k_sweep_list_exp<Op, 3><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op, c->partial);
+        else if (c->group == 2) {
+            const int groups = (d.iEnd + 1) / 2 - d.iBegin / 2;
+            k_sweep_list_g<Op, 2><<<sphk_blocks(groups), SPHK_BLOCK, 0, c->stream>>>(d, op);
+        }
+        else if (c->lanesPerParticle == 4) k_sweep_list4<Op><<<sphk_blocks(4 * (d.iEnd - d.iBegin)), SPHK_BLOCK, 0, c->stream>>>(d, op);
+        else if (c->schedule == 1) {
+            static int perSM = 0;       // resident blocks per SM of this instantiation
+            if (!perSM) {
+                cudaFuncSetAttribute(k_sweep_list_p<Op>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sweep_list_p<Op>, SPHK_BLOCK, 0) != cudaSuccess || perSM < 1) perSM = 8;
+            }
+            TileQueue tq{c->sched, c->sched + 256, sphk_blocks(d.iEnd - d.iBegin), c->numSMs};
+            int grid = c->numSMs * perSM;
+            if (grid > tq.ntiles) grid = tq.ntiles;
+            k_sweep_list_p<Op><<<grid, SPHK_BLOCK, 0, c->stream>>>(d, op, tq);
+        }
         else k_sweep_list<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     } else {
         k_sweep_cells<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
@@ -747,7 +1287,7 @@ static void ensure_scalar(sphk_ctx* c, const float* array) {
 extern "C" int sphk_boundary_mass(sphk_ctx* c, const sphk_particles* b, const int* csB, float rhoB, float R) {
     if (!c || !b || !csB || !b->mass) return SPHK_ERR_INVALID;
     if (!c->boundarySearched || b->n != c->nB) return SPHK_ERR_STATE;
-    Rec* recB = c->rec + c->capF;
+    const Rec recB = c->rec + c->capF;
     k_boundary_mass<<<sphk_blocks(c->nB), SPHK_BLOCK, 0, c->stream>>>(recB, b->mass, c->nB, csB, c->cs, c->org, c->cellLength, rhoB,
                                                                      kernel_constants(R));
     k_set_mass<<<sphk_blocks(c->nB), SPHK_BLOCK, 0, c->stream>>>(recB, b->mass, c->nB);
@@ -933,7 +1473,7 @@ extern "C" int sphk_pbd_xsph(sphk_ctx* c, const sphk_scene* s, float xc, float r
 }
 
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_push_range(Rec* __restrict__ rec, const float* __restrict__ vel, const float* __restrict__ scalar,
+k_push_range(Rec rec, const float* __restrict__ vel, const float* __restrict__ scalar,
              const float* __restrict__ pos, const float4* __restrict__ posBuild, unsigned int* __restrict__ dispMax,
              int begin, int count) {
     const int t = blockIdx.x * SPHK_BLOCK + threadIdx.x;
@@ -941,7 +1481,7 @@ k_push_range(Rec* __restrict__ rec, const float* __restrict__ vel, const float* 
     if (t < count) {
         const int i = begin + t;
         if (vel) rec_set_vel(rec + i, load3(vel, i));
-        if (scalar) rec[i].s = scalar[i];
+        if (scalar) rec_set_s(rec + i, scalar[i]);
         if (pos) {
             const float3 p = load3(pos, i);
             rec_set_pos(rec + i, p);
@@ -1026,6 +1566,7 @@ extern "C" int sphk_build_neighbor_list(sphk_ctx* c, const sphk_scene* s) {
 
 extern "C" int sphk_get_neighbor_list(sphk_ctx* c, const sphk_scene* s, int* counts_out, int* entries_out) {
     SPHK_CHECK_SCENE(c, s);
+    if (c->tile) return SPHK_ERR_STATE;     // tile lists hold 16-bit window slots: use sphk_get_tile_lists
     const DevScene d = dev_scene(c, s);
     const int rc = ensure_list(c, d);
     if (rc != SPHK_OK) return rc;
@@ -1043,7 +1584,8 @@ extern "C" int sphk_list_stats(sphk_ctx* c, const sphk_scene* s, long long out_h
     if (rc != SPHK_OK) return rc;
     unsigned long long* dev = reinterpret_cast<unsigned long long*>(c->partial);
     SPHK_CUDA_TRY(cudaMemsetAsync(dev, 0, 3 * sizeof(unsigned long long), c->stream));
-    k_list_stats<<<256, 256, 0, c->stream>>>(c->cnt + c->listBegin, c->listEnd - c->listBegin, c->kmax, dev);
+    if (c->group == 2 && !c->tile) k_list_stats<<<256, 256, 0, c->stream>>>(c->cnt + c->listBegin / 2, (c->listEnd + 1) / 2 - c->listBegin / 2, d.kmax, dev);
+    else k_list_stats<<<256, 256, 0, c->stream>>>(c->cnt + c->listBegin, c->listEnd - c->listBegin, c->kmax, dev);
     c->launches++;
     unsigned long long h[3];
     SPHK_CUDA_TRY(cudaMemcpyAsync(h, dev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

@@ -23,8 +23,34 @@
 #include "SPHSystem.h"
 #include "sph_app.h"
 
+// One batch in flight through the pipelined host-buffer path (sph_app_submit / sph_app_wait)
+struct sph_batch {
+    float3* dIn[2] = {nullptr, nullptr};     // device staging: pos, vel of the batch
+    float3* dOut[2] = {nullptr, nullptr};    // device staging of the result: pos, vel
+    float* dOutDensity = nullptr;
+    cudaEvent_t uploaded = nullptr, computed = nullptr;
+    float* hPos = nullptr; float* hVel = nullptr; float* hDensity = nullptr;   // where the result goes (host)
+    bool pending = false;                    // uploaded, not yet stepped
+    float ms = 0.f;
+};
+
 struct sph_app {
     std::shared_ptr<SPHSystem> system;
+    // pipelined path (created on first sph_app_submit)
+    cudaStream_t copyStream = nullptr;
+    sph_batch batch[2];
+    unsigned long long submitted = 0;
+    bool pipeReady = false;
+    ~sph_app() {
+        if (pipeReady) {
+            cudaStreamSynchronize(copyStream);
+            for (auto& b : batch) {
+                cudaFree(b.dIn[0]); cudaFree(b.dIn[1]); cudaFree(b.dOut[0]); cudaFree(b.dOut[1]); cudaFree(b.dOutDensity);
+                cudaEventDestroy(b.uploaded); cudaEventDestroy(b.computed);
+            }
+            cudaStreamDestroy(copyStream);
+        }
+    }
 };
 
 static std::vector<float3> to_float3(const float* xyz, int n) {
@@ -113,6 +139,87 @@ extern "C" int sph_app_upload_fluid(sph_app* app, const float* pos, const float*
     int bad = 0;
     if (pos) bad |= cudaMemcpy(f->getPosPtr(), pos, n * sizeof(float3), cudaMemcpyHostToDevice) != cudaSuccess;
     if (vel) bad |= cudaMemcpy(f->getVelPtr(), vel, n * sizeof(float3), cudaMemcpyHostToDevice) != cudaSuccess;
+    return bad;
+}
+
+// ---- pipelined host-buffer stepping -------------------------------------------------------------------------------
+// The reference's own call sites move data with synchronous cudaMemcpy through the raw accessors (Particles.h:24,
+// vbo.cu:48).  A caller that feeds a batch of particle states from host memory and reads every result back pays
+// ~2 ms of PCIe time per 2M-particle step that way.  sph_app_submit overlaps those copies with the previous batch's
+// step: uploads and downloads run on a copy stream into / out of device staging buffers, the step itself only adds
+// two device-to-device copies.  Only public accessors and the CUDA runtime are used, so this builds on either engine.
+static bool pipe_init(sph_app* app) {
+    if (app->pipeReady) return true;
+    const size_t n = app->system->getFluids()->size();
+    if (cudaStreamCreateWithFlags(&app->copyStream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    for (auto& b : app->batch) {
+        bool ok = true;
+        for (int k = 0; k < 2; ++k) {
+            ok = ok && cudaMalloc(reinterpret_cast<void**>(&b.dIn[k]), n * sizeof(float3)) == cudaSuccess;
+            ok = ok && cudaMalloc(reinterpret_cast<void**>(&b.dOut[k]), n * sizeof(float3)) == cudaSuccess;
+        }
+        ok = ok && cudaMalloc(reinterpret_cast<void**>(&b.dOutDensity), n * sizeof(float)) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&b.uploaded, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&b.computed, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) return false;
+    }
+    app->pipeReady = true;
+    return true;
+}
+
+// steps the batch in `slot` (its upload has been enqueued) and enqueues the download of its result
+static int pipe_run(sph_app* app, int slot) {
+    sph_batch& b = app->batch[slot];
+    if (!b.pending) return 0;
+    const auto f = app->system->getFluids();
+    const size_t n = f->size();
+    int bad = 0;
+    // legacy default stream: ordered with everything the engines enqueue (the reference uses it throughout; this
+    // repository's engine stream is a blocking stream)
+    bad |= cudaStreamWaitEvent(nullptr, b.uploaded, 0) != cudaSuccess;
+    bad |= cudaMemcpyAsync(f->getPosPtr(), b.dIn[0], n * sizeof(float3), cudaMemcpyDeviceToDevice, nullptr) != cudaSuccess;
+    bad |= cudaMemcpyAsync(f->getVelPtr(), b.dIn[1], n * sizeof(float3), cudaMemcpyDeviceToDevice, nullptr) != cudaSuccess;
+    b.ms = app->system->step();
+    bad |= cudaMemcpyAsync(b.dOut[0], f->getPosPtr(), n * sizeof(float3), cudaMemcpyDeviceToDevice, nullptr) != cudaSuccess;
+    bad |= cudaMemcpyAsync(b.dOut[1], f->getVelPtr(), n * sizeof(float3), cudaMemcpyDeviceToDevice, nullptr) != cudaSuccess;
+    bad |= cudaMemcpyAsync(b.dOutDensity, f->getDensityPtr(), n * sizeof(float), cudaMemcpyDeviceToDevice, nullptr) != cudaSuccess;
+    bad |= cudaEventRecord(b.computed, nullptr) != cudaSuccess;
+    bad |= cudaStreamWaitEvent(app->copyStream, b.computed, 0) != cudaSuccess;
+    if (b.hPos) bad |= cudaMemcpyAsync(b.hPos, b.dOut[0], n * sizeof(float3), cudaMemcpyDeviceToHost, app->copyStream) != cudaSuccess;
+    if (b.hVel) bad |= cudaMemcpyAsync(b.hVel, b.dOut[1], n * sizeof(float3), cudaMemcpyDeviceToHost, app->copyStream) != cudaSuccess;
+    if (b.hDensity) bad |= cudaMemcpyAsync(b.hDensity, b.dOutDensity, n * sizeof(float), cudaMemcpyDeviceToHost, app->copyStream) != cudaSuccess;
+    b.pending = false;
+    return bad;
+}
+
+extern "C" int sph_app_submit(sph_app* app, const float* pos_in, const float* vel_in, float* pos_out, float* vel_out,
+                              float* density_out) {
+    if (!app || !pos_in || !vel_in || !pipe_init(app)) return 1;
+    const size_t n = app->system->getFluids()->size();
+    const int slot = static_cast<int>(app->submitted & 1ull);
+    sph_batch& b = app->batch[slot];
+    int bad = 0;
+    // (the slot's previous batch was stepped during the previous submit; its staging is free once that step has run.
+    // Its download reads dOut, which this batch overwrites only after ITS step -- two submits later on this slot --
+    // and the copy stream is in order, so the earlier download is complete by then.)
+    bad |= cudaMemcpyAsync(b.dIn[0], pos_in, n * sizeof(float3), cudaMemcpyHostToDevice, app->copyStream) != cudaSuccess;
+    bad |= cudaMemcpyAsync(b.dIn[1], vel_in, n * sizeof(float3), cudaMemcpyHostToDevice, app->copyStream) != cudaSuccess;
+    bad |= cudaEventRecord(b.uploaded, app->copyStream) != cudaSuccess;
+    b.hPos = pos_out; b.hVel = vel_out; b.hDensity = density_out;
+    b.pending = true;
+    app->submitted++;
+    // while this upload is in flight, step the batch submitted before it
+    bad |= pipe_run(app, slot ^ 1);
+    return bad;
+}
+
+extern "C" int sph_app_wait(sph_app* app) {
+    if (!app || !app->pipeReady) return 0;
+    int bad = 0;
+    const int last = static_cast<int>((app->submitted + 1) & 1ull);     // slot of the most recent submit
+    bad |= pipe_run(app, last ^ 1);
+    bad |= pipe_run(app, last);
+    bad |= cudaStreamSynchronize(app->copyStream) != cudaSuccess;
     return bad;
 }
 

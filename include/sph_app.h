@@ -55,6 +55,17 @@ int   sph_app_download_fluid(sph_app* app, float* pos_xyz, float* vel_xyz, float
 int   sph_app_download_boundary(sph_app* app, float* pos_xyz, float* mass, int* particle2cell);
 /* Host->device overwrite of fluid pos / vel through getPosPtr / getVelPtr (either may be NULL). */
 int   sph_app_upload_fluid(sph_app* app, const float* pos_xyz, const float* vel_xyz);
+/* Pipelined host-buffer stepping: one call = "advance the particle state held in HOST memory (pos_in, vel_in) by one
+ * SPHSystem::step() and deliver pos / vel / density of the result to HOST memory".  The upload of this batch and the
+ * download of the previous result overlap the previous batch's step (copy stream + device staging; the step itself
+ * only adds device-to-device copies), so a stream of batches costs one step per batch instead of step + PCIe time.
+ * Host buffers should be pinned (cudaHostAlloc / torch pin_memory) and must stay valid until sph_app_wait() returns;
+ * results of batch k are complete after the call that submits batch k+2, or after sph_app_wait().  Output pointers
+ * may be NULL.  Returns 0 on success. */
+int   sph_app_submit(sph_app* app, const float* pos_in_xyz, const float* vel_in_xyz,
+                     float* pos_out_xyz, float* vel_out_xyz, float* density_out);
+/* Steps every submitted batch that has not run yet and waits for all downloads. */
+int   sph_app_wait(sph_app* app);
 /* Name of the engine underneath: "reference-cuda" or "b200-native". */
 const char* sph_app_engine(void);
 
