@@ -47,6 +47,8 @@ ALG_BYTES = {  # algorithmic HBM bytes per fluid particl
     "density_alpha+color_grad": 36,   # R pos12+mass4, W density4 alpha4 colorGrad12
     "density+color_grad": 32,         # R pos12+mass4, W density4 colorGrad12
     "viscosity+surface": 76,          # viscosity 40 + surface 52 - shared pos/mass 16
+    # density/alpha + colour gradient + first divergence error: R pos12 vel12 mass4, W density4 alpha4 colorGrad12 error4 stiff4
+    "density_alpha+color_grad+div_error": 56,
 }
 SCENE_OF_N = {1: "2m", 2: "4m", 4: "8m", 8: "16m"}
 
@@ -234,7 +236,8 @@ def workload_name(scene_name: str, solver: str) -> str:
 def timed_kernels(solver: str):
     """(label, method name on SphkSystem, algorithmic bytes key) of the sweeps timed individually."""
     if solver == "dfsph":
-        return [("density: computeDensityAlpha + colour gradient (fused sweep)", "fused_density_color_grad", "density_alpha+color_grad"),
+        return [("density: computeDensityAlpha + colour gradient + first divergence error (fused sweep)", "fused_density_alpha_div_error",
+                 "density_alpha+color_grad+div_error"),
                 ("dfsph_div_error", "dfsph_div_error", "dfsph_error"), ("dfsph_div_correct", "dfsph_div_correct", "dfsph_correct"),
                 ("dfsph_den_error", "dfsph_den_error", "dfsph_error"), ("dfsph_den_correct", "dfsph_den_correct", "dfsph_correct"),
                 ("viscosity + surface (fused sweep)", "fused_viscosity_surface", "viscosity+surface")]

@@ -1532,6 +1532,27 @@ extern "C" int sphk_fused_dfsph_density_alpha_color_grad(sphk_ctx* c, const sphk
     return run_sweep(c, s, op);
 }
 
+// computeDensityAlpha_CUDA (+ computeColorGrad_CUDA) + the FIRST computeDivergenceError_CUDA of correctDivergenceError
+// (DFSPHSolver.cu:341): the error sum needs the neighbours' positions and velocities only, and its epilogue needs the
+// particle's own density and alpha, which the same thread has just formed -- one pass over the neighbour list less.
+extern "C" int sphk_fused_dfsph_density_alpha_div_error(sphk_ctx* c, const sphk_scene* s, float* alpha, float* color_grad_or_null,
+                                                       float rho0, float rhoB, float* error, float* stiff, float dt) {
+    SPHK_CHECK_SCENE(c, s);
+    if (!alpha || !error || !stiff || !s->fluid.density) return SPHK_ERR_INVALID;
+    const OpDfsphError<false> err{c->rec, s->fluid.density, alpha, error, stiff, nullptr, dt, rho0};
+    int rc;
+    if (color_grad_or_null) {
+        OpPair<OpPair<OpDensityAlpha, OpColorGrad>, OpDfsphError<false>> op{
+            OpPair<OpDensityAlpha, OpColorGrad>{OpDensityAlpha{s->fluid.density, alpha}, OpColorGrad{color_grad_or_null, rho0, rhoB}}, err};
+        rc = run_sweep(c, s, op);
+    } else {
+        OpPair<OpDensityAlpha, OpDfsphError<false>> op{OpDensityAlpha{s->fluid.density, alpha}, err};
+        rc = run_sweep(c, s, op);
+    }
+    c->sTag = stiff;
+    return rc;
+}
+
 extern "C" int sphk_fused_viscosity_surface(sphk_ctx* c, const sphk_scene* s, float* delta_v, const float* color_grad,
                                             float rho0, float visc, float dt, float kappa, float airP) {
     SPHK_CHECK_SCENE(c, s);

@@ -196,6 +196,13 @@ class SphkOps:
             check(self.L.sphk_fused_density_color_grad(self.ctx, self._s(), _ptr(self.color_grad_buf), C.c_float(self.p.rho0),
                                                        C.c_float(self.p.rho_boundary)), "sphk_fused_density_color_grad")
 
+    def fused_density_alpha_div_error(self, with_color_grad: bool):
+        check(self.L.sphk_fused_dfsph_density_alpha_div_error(self.ctx, self._s(), _ptr(self.alpha),
+                                                              _ptr(self.color_grad_buf) if with_color_grad else None,
+                                                              C.c_float(self.p.rho0), C.c_float(self.p.rho_boundary), _ptr(self.error),
+                                                              _ptr(self.kappa), C.c_float(self.p.dt)),
+              "sphk_fused_dfsph_density_alpha_div_error")
+
     def fused_viscosity_surface(self):
         check(self.L.sphk_fused_viscosity_surface(self.ctx, self._s(), _ptr(self.buffer3), _ptr(self.color_grad_buf),
                                                   C.c_float(self.p.rho0), C.c_float(self.p.visc), C.c_float(self.p.dt),
@@ -299,12 +306,14 @@ class SphkOps:
         self.set_use_list(self.use_list)
         n, rho0 = self.n_total(), self.p.rho0
         fused = self.fused and self._surface_enabled()
-        if fused:
-            self._run(lambda: self.fused_density_color_grad(True), "array", self.color_grad_buf)
+        if self.fused:               # density/alpha (+ colour gradient) + the first divergence error (:341) in one sweep
+            self._run(lambda: self.fused_density_alpha_div_error(fused), "scalar", self.kappa)
+            if fused:
+                self.sync_array(self.color_grad_buf)
         else:
             self.dfsph_density_alpha()
+            self._run(self.dfsph_div_error, "scalar", self.kappa)
         total, it = 3.4e38, 0        # correctDivergenceError :331-363
-        self._run(self.dfsph_div_error, "scalar", self.kappa)
         while (it < 1 or total > self.div_thr * n * rho0) and it < self.max_iter:
             self._run(self.dfsph_div_correct, "vel")
             self._run(self.dfsph_div_error, "scalar", self.kappa)

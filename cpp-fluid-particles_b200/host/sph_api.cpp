@@ -177,9 +177,15 @@ void DFSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_
     if (!beginStep(fluids, boundaries, cellStartFluid, cellStartBoundary, radius, true, 0)) return;
     const int num = static_cast<int>(fluids->size());
     const bool surface = surfaceTensionIntensity > EPSILON || airPressure > EPSILON;
-    if (fusedSweeps_) densityAndColorGrad(alpha.addr(), rho0, rhoB, surface);   // colour gradient: positions only
-    else check(sphk_dfsph_density_alpha(current_.ctx, &current_.abi, alpha.addr()), "sphk_dfsph_density_alpha");
-    itDiv_ = correctDivergenceError(rho0, dt, divergenceErrorThreshold, maxIter, num);
+    if (fusedSweeps_) {
+        // density/alpha + colour gradient (positions only) + the first divergence error of :341 in one sweep
+        check(sphk_fused_dfsph_density_alpha_div_error(current_.ctx, &current_.abi, alpha.addr(), surface ? colorGradBuffer() : nullptr,
+                                                       rho0, rhoB, error.addr(), bufferFloat.addr(), dt),
+              "sphk_fused_dfsph_density_alpha_div_error");
+    } else {
+        check(sphk_dfsph_density_alpha(current_.ctx, &current_.abi, alpha.addr()), "sphk_dfsph_density_alpha");
+    }
+    itDiv_ = correctDivergenceError(rho0, dt, divergenceErrorThreshold, maxIter, num, fusedSweeps_);
     force(fluids, dt, G);
     if (fusedSweeps_) {
         diffuseAndSurface(rho0, rhoB, visc, dt, surfaceTensionIntensity, airPressure, surface, true);
@@ -197,12 +203,13 @@ void DFSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_
 // DFSPHSolver::correctDivergenceError, DFSPHSolver.cu:331-363.  With a negative threshold the loop test
 // `totalError > thr*num*rho0` is true for every possible error sum, so the (host-synchronising)
 // reduction is skipped: same iteration count as the reference, no pipeline bubble (Q11).
-int DFSPHSolver::correctDivergenceError(float rho0, float dt, float errorThreshold, int maxIter_, int num) {
+int DFSPHSolver::correctDivergenceError(float rho0, float dt, float errorThreshold, int maxIter_, int num, bool firstErrorDone) {
     auto totalError = std::numeric_limits<float>::max();
     auto iter = 0;
     sphk_ctx* ctx = current_.ctx;
-    check(sphk_dfsph_div_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0),
-          "sphk_dfsph_div_error");
+    if (!firstErrorDone)
+        check(sphk_dfsph_div_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0),
+              "sphk_dfsph_div_error");
     while ((iter < 1 || totalError > errorThreshold * num * rho0) && iter < maxIter_) {
         check(sphk_dfsph_div_correct(ctx, &current_.abi, bufferFloat.addr()), "sphk_dfsph_div_correct");
         check(sphk_dfsph_div_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0),

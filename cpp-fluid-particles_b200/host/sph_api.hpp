@@ -201,6 +201,7 @@ protected:
                            bool surface, bool colorGradReady);
     bool fusedSweeps_ = true;
     unsigned int configEpoch_ = 0;
+    float* colorGradBuffer() const { return reinterpret_cast<float*>(bufferColorGrad.addr()); }
     bool beginStep(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
                    const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float radius,
                    bool neighborList, int listSkinPermille);
@@ -231,7 +232,7 @@ protected:
                         const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float rho0,
                         int3 cellSize, float cellLength, float radius, float dt, float errorThreshold, int maxIter);
 private:
-    int correctDivergenceError(float rho0, float dt, float errorThreshold, int maxIter, int num);
+    int correctDivergenceError(float rho0, float dt, float errorThreshold, int maxIter, int num, bool firstErrorDone);
     DArray<float> alpha;
     DArray<float> bufferFloat;     // the stiffness kappa of the paper
     DArray<int> bufferInt;         // kept for layout parity; the re-sort it served is sphk_permute now

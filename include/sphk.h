@@ -173,6 +173,11 @@ int sphk_fused_density_color_grad(sphk_ctx* ctx, const sphk_scene* s, float* col
 /* computeDensityAlpha_CUDA + computeColorGrad_CUDA */
 int sphk_fused_dfsph_density_alpha_color_grad(sphk_ctx* ctx, const sphk_scene* s, float* alpha, float* color_grad,
                                               float rho0, float rho_boundary);
+/* computeDensityAlpha_CUDA (+ computeColorGrad_CUDA when color_grad != NULL) + the first computeDivergenceError_CUDA of
+ * DFSPHSolver::correctDivergenceError (DFSPHSolver.cu:341), which reads the velocities the density sweep leaves
+ * untouched and, per particle, the density and alpha that particle has just computed. */
+int sphk_fused_dfsph_density_alpha_div_error(sphk_ctx* ctx, const sphk_scene* s, float* alpha, float* color_grad_or_null,
+                                             float rho0, float rho_boundary, float* error, float* stiff, float dt);
 /* viscosity_CUDA (+ vel += deltaV) followed by surfaceTensionAndAirPressure_CUDA.  delta_v and color_grad must be
  * distinct buffers (the reference reuses one buffer for both because it runs them one after the other). */
 int sphk_fused_viscosity_surface(sphk_ctx* ctx, const sphk_scene* s, float* delta_v, const float* color_grad,
