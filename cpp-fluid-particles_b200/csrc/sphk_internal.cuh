@@ -64,6 +64,8 @@ struct sphk_ctx {
     int actBegin = 0, actCount = -1; // active (owned) range of the sweeps; -1: all
     int kmax = 96;
     bool useList = true;
+    bool stagedBuild = true;         // build the list from candidate windows staged in shared memory by bulk copies (default);
+                                     // false: candidates read from global memory (k_build_list)
     bool simpleBuild = false;        // build the list with the generic cell walk (test reference of k_build_list)
     float skin = 0.f;                // neighbour-list skin as a fraction of R (PBD: positions move inside a step)
     bool listHasSkin = false;        // the current list was built with a skin and displacement is being tracked

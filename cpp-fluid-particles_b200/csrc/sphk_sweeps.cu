@@ -630,6 +630,8 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list_g(const DevScene s, c
 // tile as part of a full line instead of ~3.3 times as a lone 32-byte sector), and half the list traffic.
 // A tile whose windows exceed SPHK_TILE_CAP records, and particles outside the grid, fall back to the exact cell walk
 // (their count is stored as kmax + 1).
+__device__ __forceinline__ void build_particle_global(const DevScene& s, int i, float4 lo, int* __restrict__ nbr, int* __restrict__ cnt,
+                                                      float4* __restrict__ posBuild);
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return static_cast<unsigned int>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -652,11 +654,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int 
 
 // thread 0: prefix sums of the window lengths; stages the windows when they fit.  Returns nothing; sPre[18] = total.
 __device__ __forceinline__ void tile_stage(const DevScene& s, const int2* sWin, int* sPre, float4* smA, float4* smB, bool wantB,
-                                           unsigned long long* bar) {
+                                           unsigned long long* bar, int cap = SPHK_TILE_CAP) {
     int t = 0;
     for (int w = 0; w < SPHK_TILE_WINS; ++w) { sPre[w] = t; t += sWin[w].y; }
     sPre[SPHK_TILE_WINS] = t;
-    if (t > SPHK_TILE_CAP) return;
+    if (t > cap) return;
     smA[t] = make_float4(1.0e6f, 1.0e6f, 1.0e6f, 0.f);           // the dummy slot: list padding, contributes exactly 0
     if (wantB) smB[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t == 0) return;
@@ -696,6 +698,21 @@ __device__ __forceinline__ void build_range_tile(const float4* smA, int slot0, i
     }
 }
 
+// the 18 windows of the tile whose particles occupy cells [cA, cB] (thread w < 18 computes window w)
+__device__ __forceinline__ int2 tile_window(const DevScene& s, int w, int cA, int cB, int ncells) {
+    if (cB < 0) return make_int2(0, 0);
+    const int r = w % 9;
+    const bool isB = w >= 9;
+    const long long off = (static_cast<long long>(r / 3 - 1) * s.cs.y + (r % 3 - 1)) * s.cs.z;
+    long long cl = cA + off - 1, ch = cB + off + 1;
+    if (cl < 0) cl = 0;
+    if (ch > ncells - 1) ch = ncells - 1;
+    if (cl > ch) return make_int2(0, 0);
+    const int* cs = isB ? s.csB : s.csF;
+    const int a = cs[cl], b = cs[ch + 1];
+    return make_int2(a + (isB ? s.bOff : 0), b - a);
+}
+
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_build_tile(const DevScene s, unsigned short* __restrict__ nbr16, int* __restrict__ cnt, float4* __restrict__ posBuild,
              int2* __restrict__ tileWin) {
@@ -720,20 +737,7 @@ k_build_tile(const DevScene s, unsigned short* __restrict__ nbr16, int* __restri
     }
     __syncthreads();
     if (threadIdx.x < SPHK_TILE_WINS) {
-        int2 w = make_int2(0, 0);
-        if (sMax >= 0) {
-            const int r = threadIdx.x % 9;
-            const bool isB = threadIdx.x >= 9;
-            const long long off = (static_cast<long long>(r / 3 - 1) * s.cs.y + (r % 3 - 1)) * s.cs.z;
-            long long cl = sMin + off - 1, ch = sMax + off + 1;
-            if (cl < 0) cl = 0;
-            if (ch > ncells - 1) ch = ncells - 1;
-            if (cl <= ch) {
-                const int* cs = isB ? s.csB : s.csF;
-                const int a = cs[cl], b = cs[ch + 1];
-                w = make_int2(a + (isB ? s.bOff : 0), b - a);
-            }
-        }
+        const int2 w = tile_window(s, threadIdx.x, sMin, sMax, ncells);
         sWin[threadIdx.x] = w;
         tileWin[static_cast<size_t>(tile) * SPHK_TILE_WINS + threadIdx.x] = w;
     }
@@ -768,6 +772,90 @@ k_build_tile(const DevScene s, unsigned short* __restrict__ nbr16, int* __restri
     }
     cnt[i] = n;
     for (int m = n; (m & 7) && m < s.kmax; ++m) { *wp = static_cast<unsigned short>(T); ++wp; }   // pad the open batch with the dummy slot
+}
+
+// The default list builder: the tile's candidate windows are staged in shared memory exactly as above (cp.async.bulk +
+// mbarrier), the candidate tests read the staged records (lanes of one cell read the same slot: a broadcast), and the
+// list it writes is the int32 per-particle list of k_build_list (global record indices, int4 batches, padded with the
+// particle itself) -- entry for entry, so the list sweeps and the list tests do not care which builder ran.
+// A tile whose windows exceed the staging capacity, and particles outside the grid, take the global-memory path.
+#define SPHK_BUILD_CAP 2047
+__device__ __forceinline__ void build_range_staged(const float4* smA, int slot0, int j0g, int count, float3 xi, float r2list, int self,
+                                                   int kmax, int& n, int*& wp, long long jump) {
+    for (int k0 = 0; k0 < count; k0 += 32) {
+        const int len = min(32, count - k0);
+        const float4* base = smA + slot0 + k0;
+        unsigned int mask = 0u;
+#pragma unroll 4
+        for (int k = 0; k < len; ++k) {
+            const float3 d = xi - xyz(base[k]);
+            mask |= (dot3(d, d) <= r2list ? 1u : 0u) << k;
+        }
+        const int sf = self - (j0g + k0);
+        if (sf >= 0 && sf < 32) mask &= ~(1u << sf);
+        while (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (n < kmax) *wp = j0g + k0 + k;
+            wp += ((n & 3) == 3) ? jump : 1;
+            ++n;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_build_list_staged(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, float4* __restrict__ posBuild) {
+    extern __shared__ float4 smA[];                 // [SPHK_BUILD_CAP + 1]
+    __shared__ unsigned long long bar;
+    __shared__ int sMin, sMax;
+    __shared__ int2 sWin[SPHK_TILE_WINS];
+    __shared__ int sPre[SPHK_TILE_WINS + 1];
+    const int tile = s.iBegin / SPHK_BLOCK + blockIdx.x;
+    const int i = tile * SPHK_BLOCK + threadIdx.x;
+    const bool have = i < s.nF;
+    const int ncells = s.cs.x * s.cs.y * s.cs.z;
+    if (threadIdx.x == 0) { sMin = 0x7fffffff; sMax = -1; }
+    __syncthreads();
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cx = 0, cy = 0, cz = 0, c = ncells;
+    if (have) {
+        lo = rec_lo(s.rec + i);
+        cx = cell_coord(lo.x, s.cellLength) - s.org.x; cy = cell_coord(lo.y, s.cellLength) - s.org.y; cz = cell_coord(lo.z, s.cellLength) - s.org.z;
+        c = cell_index(cx, cy, cz, s.cs);
+        if (c < ncells) { atomicMin(&sMin, c); atomicMax(&sMax, c); }
+    }
+    __syncthreads();
+    if (threadIdx.x < SPHK_TILE_WINS) sWin[threadIdx.x] = tile_window(s, threadIdx.x, sMin, sMax, ncells);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_stage(s, sWin, sPre, smA, nullptr, false, &bar, SPHK_BUILD_CAP);
+    __syncthreads();
+    const int T = sPre[SPHK_TILE_WINS];
+    const bool staged = T <= SPHK_BUILD_CAP;
+    if (staged && T > 0) mbar_wait(&bar, 0);        // every thread: the block must not retire with bulk copies in flight
+    if (!have || i < s.iBegin || i >= s.iEnd) return;
+    if (!staged || c >= ncells) { build_particle_global(s, i, lo, nbr, cnt, posBuild); return; }
+    const float3 xi = xyz(lo);
+    const int zlo = max(cz - 1, 0), zhi = min(cz + 1, s.cs.z - 1);
+    int n = 0;
+    int* wp = nbr + static_cast<size_t>(i) * 4;
+    const long long jump = static_cast<long long>(s.nbrStride) * 4 - 3;
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+        if (x < 0 || x >= s.cs.x || y < 0 || y >= s.cs.y) continue;
+        const int c0 = (x * s.cs.y + y) * s.cs.z;
+        {
+            const int a = s.csF[c0 + zlo], b = s.csF[c0 + zhi + 1];
+            build_range_staged(smA, sPre[r] + (a - sWin[r].x), a, b - a, xi, s.r2list, i, s.kmax, n, wp, jump);
+        }
+        {
+            const int a = s.csB[c0 + zlo], b = s.csB[c0 + zhi + 1];
+            if (b > a) build_range_staged(smA, sPre[r + 9] + (a + s.bOff - sWin[r + 9].x), a + s.bOff, b - a, xi, s.r2list, -1, s.kmax, n, wp, jump);
+        }
+    }
+    cnt[i] = n;
+    for (int m = n; (m & 3) && m < s.kmax; ++m) { *wp = i; ++wp; }            // pad the open batch with the particle itself
+    if (posBuild) posBuild[i] = lo;
 }
 
 // ---- sweep ----------------------------------------------------------------------------------------------------------------
@@ -914,11 +1002,8 @@ __device__ __forceinline__ void build_range(const DevScene& s, float3 xi, int i,
     }
 }
 
-__global__ void __launch_bounds__(SPHK_BLOCK)
-k_build_list(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, float4* __restrict__ posBuild) {
-    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= s.iEnd) return;
-    const float4 lo = rec_lo(s.rec + i);
+__device__ __forceinline__ void build_particle_global(const DevScene& s, int i, float4 lo, int* __restrict__ nbr, int* __restrict__ cnt,
+                                                      float4* __restrict__ posBuild) {
     const float3 xi = xyz(lo);
     const int cx = cell_coord(lo.x, s.cellLength) - s.org.x, cy = cell_coord(lo.y, s.cellLength) - s.org.y,
               cz = cell_coord(lo.z, s.cellLength) - s.org.z;
@@ -940,6 +1025,13 @@ k_build_list(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, flo
     // pad the open batch with the particle itself: the self pair contributes exactly 0 to every operator
     for (int m = n; (m & 3) && m < s.kmax; ++m) { *wp = i; ++wp; }
     if (posBuild) posBuild[i] = lo;
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_build_list(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, float4* __restrict__ posBuild) {
+    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (i >= s.iEnd) return;
+    build_particle_global(s, i, rec_lo(s.rec + i), nbr, cnt, posBuild);
 }
 
 // Pair-list builder (SPHK_OPT_GROUP = 2): thread k builds the union list of particles 2k and 2k+1.
@@ -1214,6 +1306,12 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
     } else if (c->simpleBuild) {
         OpBuildList op{c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr};
         k_sweep_cells<OpBuildList><<<sphk_blocks(b.iEnd - b.iBegin), SPHK_BLOCK, 0, c->stream>>>(b, op);
+    } else if (c->stagedBuild) {
+        static bool attr = false;
+        const int smem = (SPHK_BUILD_CAP + 1) * 16;
+        if (!attr) { cudaFuncSetAttribute(k_build_list_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+        const int tiles = (b.iEnd + SPHK_BLOCK - 1) / SPHK_BLOCK - b.iBegin / SPHK_BLOCK;
+        k_build_list_staged<<<tiles, SPHK_BLOCK, smem, c->stream>>>(b, c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr);
     } else {
         k_build_list<<<sphk_blocks(b.iEnd - b.iBegin), SPHK_BLOCK, 0, c->stream>>>(b, c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr);
     }

@@ -80,6 +80,8 @@ enum {
                                     27 cells.  default 1 */
     SPHK_OPT_LIST_CAPACITY = 2,  /* max neighbours kept per particle; particles with more fall back
                                     to the cell walk individually.  default 96 */
+    SPHK_OPT_STAGED_LIST_BUILD = 10, /* 1 (default): the list builder stages each tile's 9 + 9 candidate windows in shared memory
+                                    (cp.async.bulk + mbarrier) and tests candidates from there; 0: candidates read from global memory */
     SPHK_OPT_SIMPLE_LIST_BUILD = 6, /* 1: build the list with the generic cell walk (reference for the tuned builder) */
     SPHK_OPT_LIST_SKIN = 5,      /* neighbour-list skin in 1/1000 of the radius (default 0).  With a skin the list
                                     stays valid while sphk_pbd_delta_pos_apply moves particles by less than skin/2
