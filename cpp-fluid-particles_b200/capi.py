@@ -35,8 +35,7 @@ SPH_APP_FUNCTIONS = [
     "sph_app_submit", "sph_app_wait",
 ]
 
-OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_LANES_PER_PARTICLE, OPT_LIST_SKIN, OPT_SIMPLE_LIST_BUILD = 1, 2, 4, 5, 6
-OPT_SCHEDULE, OPT_GROUP, OPT_TILE, OPT_STAGED_LIST_BUILD = 7, 8, 9, 10
+OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_LIST_SKIN, OPT_SIMPLE_LIST_BUILD, OPT_TILE, OPT_STAGED_LIST_BUILD = 1, 2, 5, 6, 9, 10
 
 
 class SphkGrid(C.Structure):

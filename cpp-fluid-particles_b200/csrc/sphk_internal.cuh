@@ -73,14 +73,7 @@ struct sphk_ctx {
     int tile = 0;                    // 1: tile lists -- 16-bit tile-local indices, neighbour windows staged in shared memory by
                                      // bulk copies (k_build_tile / k_sweep_tile); 0: int32 lists gathered from global memory
     int2* tileWin = nullptr;         // [tiles * 18] {first record, count} of the 9 fluid + 9 boundary windows of every tile
-    int group = 1;                   // list sweeps: particles per thread sharing ONE neighbour list (the union of their
-                                     // neighbours): 1 = a list per particle; 2 = consecutive pairs (2k, 2k+1) -- a gathered
-                                     // record serves both members, 27 % fewer gathers per particle at 1.26x the arithmetic
-    int schedule = 0;                // list sweeps: 0 = one block per 128-particle tile in launch order; 1 = persistent blocks,
-                                     // every SM works through its own contiguous chunk of tiles (L1 locality), stealing at the end
-    unsigned int* sched = nullptr;   // device: tile counter per SM [256] + finished-block counter (self-resetting)
     int numSMs = 0;
-    int lanesPerParticle = 1;        // list sweeps: 1 = thread per particle (default, faster on B200: profiles/), 4 = warp-cooperative quad
     unsigned long long searchEpoch = 0, listEpoch = ~0ull;
     int listBegin = 0, listEnd = 0;  // particle range the current list covers
     bool posDirty = false;           // positions changed since the last search

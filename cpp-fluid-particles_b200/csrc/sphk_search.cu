@@ -201,15 +201,12 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
     if (e == cudaSuccess) e = dalloc(&c->tmpF, 3 * static_cast<size_t>(max_fluid));
     if (e == cudaSuccess) e = dalloc(&c->partial, 1024);
     if (e == cudaSuccess) e = dalloc(&c->cnt, static_cast<size_t>(max_fluid));
-    if (e == cudaSuccess) e = dalloc(&c->sched, 512);
     if (e == cudaSuccess) e = dalloc(&c->tileWin, (static_cast<size_t>(max_fluid) / SPHK_BLOCK + 1) * SPHK_TILE_WINS);
     if (e == cudaSuccess) {
         int dev = 0;
         cudaGetDevice(&dev);
         e = cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, dev);
         if (c->numSMs > 256) c->numSMs = 256;
-        if (const char* v = std::getenv("SPHK_SCHEDULE")) c->schedule = v[0] == '1' ? 1 : 0;
-        if (const char* v = std::getenv("SPHK_GROUP")) c->group = v[0] == '2' ? 2 : 1;
         if (const char* v = std::getenv("SPHK_TILE")) c->tile = v[0] == '1' ? 1 : 0;
     }
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&c->pinned), 64);
@@ -228,7 +225,7 @@ extern "C" void sphk_destroy(sphk_ctx* c) {
     if (!c) return;
     cudaFree(c->keys); cudaFree(c->keysSorted); cudaFree(c->idx); cudaFree(c->idxSorted);
     cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec.a); cudaFree(c->rec.b); cudaFree(c->massRange); cudaFree(c->dispMax);
-    cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp); cudaFree(c->sched); cudaFree(c->tileWin);
+    cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp); cudaFree(c->tileWin);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
 }
@@ -254,16 +251,6 @@ extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
         if (value != 0 && value != 1) return SPHK_ERR_INVALID;
         if (value != c->tile) { c->tile = value; c->listEpoch = ~0ull; }
         return SPHK_OK;
-    case SPHK_OPT_GROUP:
-        if (value != 1 && value != 2) return SPHK_ERR_INVALID;
-        if (value != c->group) { c->group = value; c->listEpoch = ~0ull; }
-        return SPHK_OK;
-    case SPHK_OPT_SCHEDULE:
-        if (value != 0 && value != 1) return SPHK_ERR_INVALID;
-        c->schedule = value; return SPHK_OK;
-    case SPHK_OPT_LANES_PER_PARTICLE:
-        if (value != 1 && value != 4) return SPHK_ERR_INVALID;
-        c->lanesPerParticle = value; return SPHK_OK;
     default: return SPHK_ERR_INVALID;
     }
 }

@@ -427,194 +427,6 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, con
     sweep_list_particle(s, op, i);
 }
 
-// Persistent variant: tiles of SPHK_BLOCK consecutive particles are handed out per SM.  SM q owns the contiguous
-// run of tiles [q*T/S, (q+1)*T/S): the blocks resident on one SM work on adjacent tiles at the same time and on
-// the tiles of the adjacent cell columns right afterwards, so the neighbour records one tile pulled into L1 are hit
-// by the next ones (with launch-order scheduling the ~12 tiles resident on an SM are 148 tiles apart and every
-// record is fetched from L2 by ~10 different SMs; ncu: L1 hit rate 65 %, each missed sector costs a data-pipe
-// wavefront).  SMs that finish early take tiles from the following SMs' runs.  The counters reset themselves: the
-// last block to leave zeroes them for the next launch on the stream (no memset node, graph-replay safe).
-__device__ __forceinline__ unsigned int sm_id() { unsigned int r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
-
-struct TileQueue {
-    unsigned int* ctr;      // [nsm] tiles handed out of each SM's run
-    unsigned int* done;     // blocks finished
-    int ntiles, nsm;
-    __device__ __forceinline__ int lo(int q) const { return static_cast<int>((static_cast<long long>(q) * ntiles) / nsm); }
-};
-
-// Next tile for this block (all threads call; the result is block-uniform), or -1 when every run is exhausted.
-// Own run first (one atomic by thread 0).  Once it is empty the block steals: all threads look at the other runs'
-// counters at once (one round trip instead of a sequential scan) and thread 0 takes a tile from the fullest one.
-__device__ __forceinline__ int next_tile(const TileQueue& tq, int sm, bool& stealing, int* sh /* [2] shared */) {
-    if (!stealing) {
-        if (threadIdx.x == 0) {
-            const int a = tq.lo(sm), len = tq.lo(sm + 1) - a;
-            const unsigned int c = atomicAdd(tq.ctr + sm, 1u);
-            sh[0] = c < static_cast<unsigned int>(len) ? a + static_cast<int>(c) : -1;
-        }
-        __syncthreads();
-        const int t = sh[0];
-        __syncthreads();
-        if (t >= 0) return t;
-        stealing = true;
-    }
-    for (;;) {
-        if (threadIdx.x == 0) sh[1] = 0;
-        __syncthreads();
-        for (int q = threadIdx.x; q < tq.nsm; q += SPHK_BLOCK) {
-            const int len = tq.lo(q + 1) - tq.lo(q);
-            const unsigned int c = *reinterpret_cast<volatile unsigned int*>(tq.ctr + q);
-            const int rem = c < static_cast<unsigned int>(len) ? len - static_cast<int>(c) : 0;
-            if (rem > 0) atomicMax(sh + 1, (rem << 9) | q);
-        }
-        __syncthreads();
-        const int best = sh[1];
-        if (best == 0) { __syncthreads(); return -1; }
-        if (threadIdx.x == 0) {
-            const int q = best & 511;
-            const int a = tq.lo(q), len = tq.lo(q + 1) - a;
-            const unsigned int c = atomicAdd(tq.ctr + q, 1u);
-            sh[0] = c < static_cast<unsigned int>(len) ? a + static_cast<int>(c) : -1;
-        }
-        __syncthreads();
-        const int t = sh[0];
-        __syncthreads();
-        if (t >= 0) return t;
-    }
-}
-__device__ __forceinline__ void leave_queue(const TileQueue& tq) {
-    __threadfence();
-    if (atomicAdd(tq.done, 1u) == gridDim.x - 1) {
-        for (int q = 0; q < tq.nsm; ++q) tq.ctr[q] = 0u;
-        *tq.done = 0u;
-        __threadfence();
-    }
-}
-
-template <class Op>
-__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list_p(const DevScene s, const Op op, const TileQueue tq) {
-    __shared__ int sh[2];
-    const int sm = static_cast<int>(sm_id() % static_cast<unsigned int>(tq.nsm));
-    bool stealing = false;
-    for (;;) {
-        const int t = next_tile(tq, sm, stealing, sh);
-        if (t < 0) break;
-        const int i = s.iBegin + t * SPHK_BLOCK + threadIdx.x;
-        if (i < s.iEnd) sweep_list_particle(s, op, i);
-    }
-    if (threadIdx.x == 0) leave_queue(tq);
-}
-
-// Decomposition probes (tools/sweep_probe.py, SPHK_EXP=1|2|3; never used by the product path):
-//   1: gathers + list walk only (no pair arithmetic: the sum of one gathered word is kept alive)
-//   2: arithmetic only (every "neighbour" is the particle's own record, already in registers; the list is still read)
-//   3: gathers with ld.global.cg (bypass L1)
-template <class Op, int MODE>
-__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list_exp(const DevScene s, const Op op, float* sink) {
-    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= s.iEnd) return;
-    float4 lo, hi;
-    rec_full(s.rec + i, lo, hi);
-    const float3 xi = xyz(lo);
-    typename Op::Acc acc;
-    op.begin(acc, i, lo, hi, s);
-    const int n = s.cnt[i];
-    const float m0 = uniform_mass(s);
-    float keep = 0.f;
-    const int nb4 = (min(n, s.kmax) + 3) >> 2;
-    const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + i;
-    int4 jn = make_int4(i, i, i, i);
-    if (nb4 > 0) jn = __ldcs(row);
-    for (int b = 0; b < nb4; ++b) {
-        const int4 j4 = jn;
-        row += s.nbrStride;
-        if (b + 1 < nb4) jn = __ldcs(row);
-        float4 l0, h0, l1, h1, l2, h2, l3, h3;
-        if (MODE == 2) {
-            l0 = l1 = l2 = l3 = lo; h0 = h1 = h2 = h3 = hi;
-            l0.x += 1e-3f * (j4.x & 7); l1.y += 1e-3f * (j4.y & 7); l2.z += 1e-3f * (j4.z & 7); l3.x -= 1e-3f * (j4.w & 7);
-        } else if (MODE == 3) {
-            l0 = __ldcg(s.rec.a + j4.x); l1 = __ldcg(s.rec.a + j4.y); l2 = __ldcg(s.rec.a + j4.z); l3 = __ldcg(s.rec.a + j4.w);
-            h0 = h1 = h2 = h3 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (Op::kHi) { h0 = __ldcg(s.rec.b + j4.x); h1 = __ldcg(s.rec.b + j4.y); h2 = __ldcg(s.rec.b + j4.z); h3 = __ldcg(s.rec.b + j4.w); }
-        } else {
-            fetch<Op>(s, j4.x, l0, h0); fetch<Op>(s, j4.y, l1, h1); fetch<Op>(s, j4.z, l2, h2); fetch<Op>(s, j4.w, l3, h3);
-        }
-        if (MODE == 1) {
-            keep += l0.x + l1.y + l2.z + l3.w;
-            if (Op::kHi) keep += h0.x + h1.y + h2.z + h3.w;
-        } else {
-            list_pair(s, op, acc, i, xi, j4.x, l0, h0, m0);
-            list_pair(s, op, acc, i, xi, j4.y, l1, h1, m0);
-            list_pair(s, op, acc, i, xi, j4.z, l2, h2, m0);
-            list_pair(s, op, acc, i, xi, j4.w, l3, h3, m0);
-        }
-    }
-    if (MODE == 1) { if (keep == 123.456f) sink[0] = keep; }
-    else op.end(acc, i, lo, hi, s);
-}
-
-// Group variant: one thread computes G consecutive particles (G*k .. G*k+G-1) from ONE neighbour list, the union of
-// the members' neighbours in the cell walk's order.  Every gathered record is fed to all members: a candidate
-// outside a member's support contributes exactly 0 to it (W, grad W, the viscosity Laplacian and the surface-tension
-// gradient all select 0 beyond the support), so each member's sum is its own sum with zeros interleaved.  The point
-// is the L1 data pipe (ncu: 93 % busy, 35-49 % issue): consecutive particles share most of their neighbours
-// (lattice: 42 of 2x31), so gathers per particle drop by ~27 % at ~1.26x the arithmetic.
-// List padding is the far-away zero-mass dummy record (a member cannot be used: it is a real neighbour of its mates).
-template <class Op, int G>
-__device__ __forceinline__ void sweep_list_group(const DevScene& s, const Op& op, int k) {
-    int im[G]; bool on[G];
-    float4 lo[G], hi[G]; float3 xi[G];
-    typename Op::Acc acc[G];
-#pragma unroll
-    for (int m = 0; m < G; ++m) {
-        const int idx = k * G + m;
-        on[m] = idx >= s.iBegin && idx < s.iEnd;
-        im[m] = min(max(idx, s.iBegin), s.iEnd - 1);     // a masked member shadows a valid particle and writes nothing
-        rec_full(s.rec + im[m], lo[m], hi[m]);
-        xi[m] = xyz(lo[m]);
-        op.begin(acc[m], im[m], lo[m], hi[m], s);
-    }
-    int n = s.cnt[k];
-    const float m0 = uniform_mass(s);
-    if (s.dispMax && *s.dispMax > s.dispLimit) n = s.kmax + 1;     // skin exhausted: everybody walks the cells
-    if (n <= s.kmax) {
-        const int nb4 = (n + 3) >> 2;
-        const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + k;
-        int4 jn = make_int4(s.dummy, s.dummy, s.dummy, s.dummy);
-        if (nb4 > 0) jn = __ldcs(row);
-        for (int b = 0; b < nb4; ++b) {
-            const int4 j4 = jn;
-            row += s.nbrStride;
-            if (b + 1 < nb4) jn = __ldcs(row);
-            float4 l0, h0, l1, h1, l2, h2, l3, h3;
-            fetch<Op>(s, j4.x, l0, h0); fetch<Op>(s, j4.y, l1, h1); fetch<Op>(s, j4.z, l2, h2); fetch<Op>(s, j4.w, l3, h3);
-#pragma unroll
-            for (int m = 0; m < G; ++m) {
-                list_pair(s, op, acc[m], im[m], xi[m], j4.x, l0, h0, m0);
-                list_pair(s, op, acc[m], im[m], xi[m], j4.y, l1, h1, m0);
-                list_pair(s, op, acc[m], im[m], xi[m], j4.z, l2, h2, m0);
-                list_pair(s, op, acc[m], im[m], xi[m], j4.w, l3, h3, m0);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int m = 0; m < G; ++m)
-            if (on[m]) walk_cells(s, op, acc[m], im[m], lo[m], m0);   // more neighbours than the list keeps: exact fallback
-    }
-#pragma unroll
-    for (int m = 0; m < G; ++m)
-        if (on[m]) op.end(acc[m], im[m], lo[m], hi[m], s);
-}
-
-template <class Op, int G>
-__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list_g(const DevScene s, const Op op) {
-    const int k = s.iBegin / G + blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (k * G >= s.iEnd) return;
-    sweep_list_group<Op, G>(s, op, k);
-}
-
 // =================================================================================================
 // Tile lists: neighbour windows staged in shared memory (TMA bulk copies), 16-bit tile-local lists
 // =================================================================================================
@@ -928,49 +740,6 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_tile(const DevScene s, con
     op.end(acc, i, lo, hi, s);
 }
 
-// Warp-cooperative list walk: FOUR lanes per particle, lane q takes list entries 4b+q, partial sums are combined
-// with two warp shuffles at the end.  A warp therefore covers 8 consecutive particles (one cell, or two):
-//   - the four indices of a batch of one particle are one int4, the 8 particles' int4s are 128 contiguous
-//     bytes: ONE fully coalesced line per warp request (was four);
-//   - at every step the 32 gathered records are neighbours of the SAME cell at the SAME list position, i.e. a
-//     few adjacent cache lines, instead of neighbours of four different cells (~13 lines): the L1 data pipe
-//     processes one line per wavefront, and its wavefront rate is what bounds these sweeps (ncu, profiles/).
-// The sums are formed as four interleaved partial sums (not the reference's sequential order): ~3e-7 relative.
-template <class Op>
-__global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list4(const DevScene s, const Op op) {
-    const int t = blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    const int q = t & 3;
-    int i = s.iBegin + (t >> 2);
-    const bool valid = i < s.iEnd;
-    if (!valid) i = s.iEnd - 1;                 // keep the quad convergent for the shuffles below
-    float4 lo, hi;
-    rec_full(s.rec + i, lo, hi);
-    const float3 xi = xyz(lo);
-    typename Op::Acc acc;
-    op.begin(acc, i, lo, hi, s);
-    int n = s.cnt[i];
-    const float m0 = uniform_mass(s);
-    if (s.dispMax && *s.dispMax > s.dispLimit) n = s.kmax + 1;
-    if (n <= s.kmax) {
-        const int nb4 = (n + 3) >> 2;
-        const size_t step = static_cast<size_t>(s.nbrStride) * 4;
-        const int* __restrict__ row = s.nbr + static_cast<size_t>(i) * 4 + q;
-        int jn = (nb4 > 0) ? __ldcs(row) : i;
-        for (int b = 0; b < nb4; ++b) {
-            const int j = jn;
-            row += step;
-            if (b + 1 < nb4) jn = __ldcs(row);
-            float4 l, h;
-            fetch<Op>(s, j, l, h);
-            list_pair(s, op, acc, i, xi, j, l, h, m0);
-        }
-    } else if (q == 0) {
-        walk_cells(s, op, acc, i, lo, m0);      // more neighbours than the list keeps: exact fallback on one lane
-    }
-    acc.sums([](float& v) { v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); });
-    if (valid && q == 0) op.end(acc, i, lo, hi, s);
-}
-
 // Dedicated neighbour-list builder (the generic k_sweep_cells<OpBuildList> is kept as the simple reference of
 // what it computes; tests compare the two lists entry by entry).  Same candidate order as walk_cells.
 // The generic walk is issue-bound by SIMT divergence: ~15% of the candidates are hits, so with 32 lanes the
@@ -1032,78 +801,6 @@ k_build_list(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, flo
     const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= s.iEnd) return;
     build_particle_global(s, i, rec_lo(s.rec + i), nbr, cnt, posBuild);
-}
-
-// Pair-list builder (SPHK_OPT_GROUP = 2): thread k builds the union list of particles 2k and 2k+1.
-// Common case -- both members in the same cell column: the 3-cell z-windows of both merge into ONE contiguous range
-// per (dx,dy) row, every candidate is tested against both members and kept if it lies in either support; the kept
-// order is the cell walk's order, so each member sees its own neighbours in the order of its own walk.
-// Rare case (the pair straddles two columns, or a member lies outside the grid): member 0's walk keeps its own
-// neighbours, member 1's walk keeps those not already kept (a neighbour of member 0 always lies in member 0's
-// 27 cells).  Same two-phase structure as k_build_list (branch-free tests -> bit mask -> walk the set bits).
-template <int kMode /*0: hit either member; 1: hit member 0; 2: hit member 1 and not member 0*/>
-__device__ __forceinline__ void build_range2(const DevScene& s, float3 x0, float3 x1, int a, int b, int off, int& n, int*& wp,
-                                             long long jump) {
-    for (int j0 = a; j0 < b; j0 += 32) {
-        const int len = min(32, b - j0);
-        const Rec base = s.rec + off + j0;
-        unsigned int mask = 0u;
-#pragma unroll 4
-        for (int k = 0; k < len; ++k) {
-            const float3 p = xyz(rec_lo(base + k));
-            const float3 d0 = x0 - p, d1 = x1 - p;
-            const bool h0 = dot3(d0, d0) <= s.r2list, h1 = dot3(d1, d1) <= s.r2list;
-            const bool hit = kMode == 0 ? (h0 || h1) : kMode == 1 ? h0 : (h1 && !h0);
-            mask |= (hit ? 1u : 0u) << k;
-        }
-        while (mask) {
-            const int k = __ffs(mask) - 1;
-            mask &= mask - 1;
-            if (n < s.kmax) *wp = off + j0 + k;
-            wp += ((n & 3) == 3) ? jump : 1;
-            ++n;
-        }
-    }
-}
-
-template <int kMode>
-__device__ __forceinline__ void build_walk2(const DevScene& s, float3 x0, float3 x1, int cx, int cy, int zlo, int zhi, int& n, int*& wp,
-                                            long long jump) {
-    if (zlo > zhi) return;
-#pragma unroll 1
-    for (int r = 0; r < 9; ++r) {
-        const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
-        if (x < 0 || x >= s.cs.x || y < 0 || y >= s.cs.y) continue;
-        const int c0 = (x * s.cs.y + y) * s.cs.z;
-        build_range2<kMode>(s, x0, x1, s.csF[c0 + zlo], s.csF[c0 + zhi + 1], 0, n, wp, jump);
-        build_range2<kMode>(s, x0, x1, s.csB[c0 + zlo], s.csB[c0 + zhi + 1], s.bOff, n, wp, jump);
-    }
-}
-
-__global__ void __launch_bounds__(SPHK_BLOCK)
-k_build_list2(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, float4* __restrict__ posBuild) {
-    const int k = s.iBegin / 2 + blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    const int i0 = 2 * k;
-    if (i0 >= s.iEnd) return;
-    const int i1 = min(i0 + 1, s.nF - 1);           // odd particle count: the last pair is (i, i)
-    const float4 lo0 = rec_lo(s.rec + i0), lo1 = rec_lo(s.rec + i1);
-    const float3 x0 = xyz(lo0), x1 = xyz(lo1);
-    const int cx0 = cell_coord(lo0.x, s.cellLength) - s.org.x, cy0 = cell_coord(lo0.y, s.cellLength) - s.org.y,
-              cz0 = cell_coord(lo0.z, s.cellLength) - s.org.z;
-    const int cx1 = cell_coord(lo1.x, s.cellLength) - s.org.x, cy1 = cell_coord(lo1.y, s.cellLength) - s.org.y,
-              cz1 = cell_coord(lo1.z, s.cellLength) - s.org.z;
-    int n = 0;
-    int* wp = nbr + static_cast<size_t>(k) * 4;
-    const long long jump = static_cast<long long>(s.nbrStride) * 4 - 3;
-    if (cx0 == cx1 && cy0 == cy1) {
-        build_walk2<0>(s, x0, x1, cx0, cy0, max(min(cz0, cz1) - 1, 0), min(max(cz0, cz1) + 1, s.cs.z - 1), n, wp, jump);
-    } else {
-        build_walk2<1>(s, x0, x1, cx0, cy0, max(cz0 - 1, 0), min(cz0 + 1, s.cs.z - 1), n, wp, jump);
-        build_walk2<2>(s, x0, x1, cx1, cy1, max(cz1 - 1, 0), min(cz1 + 1, s.cs.z - 1), n, wp, jump);
-    }
-    cnt[k] = n;
-    for (int m = n; (m & 3) && m < s.kmax; ++m) { *wp = s.dummy; ++wp; }     // pad the open batch with the dummy record
-    if (posBuild) { posBuild[i0] = lo0; if (i1 != i0) posBuild[i1] = lo1; }
 }
 
 // computeBoundaryMass_CUDA, SPHSystem.cu:79-105: boundary particles against the boundary set only
@@ -1262,12 +959,9 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
     d.rec = c->rec; d.csF = s->cell_start_fluid; d.csB = s->cell_start_boundary;
     d.nbr = c->nbr; d.cnt = c->cnt; d.massRange = c->massRange;
     d.nF = c->nF; d.bOff = c->capF;
-    // pair lists: half as many lists, each up to twice as long (same storage)
-    d.nbrStride = c->group == 2 ? (c->capF + 1) / 2 : c->capF;
-    d.kmax = c->group == 2 ? 2 * c->kmax : c->kmax;
+    d.nbrStride = c->capF; d.kmax = c->kmax;
     d.dummy = c->capF + c->capB;
     d.tileWin = c->tileWin;
-    if (c->tile) { d.nbrStride = c->capF; d.kmax = c->kmax; }
     d.cs = c->cs; d.org = c->org; d.cellLength = c->cellLength;
     d.iBegin = c->actCount < 0 ? 0 : c->actBegin;
     d.iEnd = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
@@ -1300,9 +994,6 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
         const int tiles = (b.iEnd + SPHK_BLOCK - 1) / SPHK_BLOCK - b.iBegin / SPHK_BLOCK;
         k_build_tile<<<tiles, SPHK_BLOCK, smem, c->stream>>>(b, reinterpret_cast<unsigned short*>(c->nbr), c->cnt,
                                                               c->listHasSkin ? c->snapA : nullptr, c->tileWin);
-    } else if (c->group == 2) {
-        const int groups = (b.iEnd + 1) / 2 - b.iBegin / 2;
-        k_build_list2<<<sphk_blocks(groups), SPHK_BLOCK, 0, c->stream>>>(b, c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr);
     } else if (c->simpleBuild) {
         OpBuildList op{c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr};
         k_sweep_cells<OpBuildList><<<sphk_blocks(b.iEnd - b.iBegin), SPHK_BLOCK, 0, c->stream>>>(b, op);
@@ -1336,32 +1027,12 @@ template <class Op> static int run_sweep(sphk_ctx* c, const sphk_scene* s, const
             d.dispMax = c->dispMax;
             memcpy(&d.dispLimit, &lim, sizeof(float));
         }
-        static const int expMode = [] { const char* v = std::getenv("SPHK_EXP"); return v ? atoi(v) : 0; }();
-        if (c->tile && expMode == 0) {
+        if (c->tile) {
             static bool attr = false;
             const int smem = (SPHK_TILE_CAP + 1) * 16 * (Op::kHi ? 2 : 1);
             if (!attr) { cudaFuncSetAttribute(k_sweep_tile<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
             const int tiles = (d.iEnd + SPHK_BLOCK - 1) / SPHK_BLOCK - d.iBegin / SPHK_BLOCK;
             k_sweep_tile<Op><<<tiles, SPHK_BLOCK, smem, c->stream>>>(d, op);
-        }
-        else if (expMode == 1) k_sweep_list_exp<Op, 1><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op, c->partial);
-        else if (expMode == 2) k_sweep_list_exp<Op, 2><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op, c->partial);
-        else if (expMode == 3) k_sweep_list_exp<Op, 3><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op, c->partial);
-        else if (c->group == 2) {
-            const int groups = (d.iEnd + 1) / 2 - d.iBegin / 2;
-            k_sweep_list_g<Op, 2><<<sphk_blocks(groups), SPHK_BLOCK, 0, c->stream>>>(d, op);
-        }
-        else if (c->lanesPerParticle == 4) k_sweep_list4<Op><<<sphk_blocks(4 * (d.iEnd - d.iBegin)), SPHK_BLOCK, 0, c->stream>>>(d, op);
-        else if (c->schedule == 1) {
-            static int perSM = 0;       // resident blocks per SM of this instantiation
-            if (!perSM) {
-                cudaFuncSetAttribute(k_sweep_list_p<Op>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sweep_list_p<Op>, SPHK_BLOCK, 0) != cudaSuccess || perSM < 1) perSM = 8;
-            }
-            TileQueue tq{c->sched, c->sched + 256, sphk_blocks(d.iEnd - d.iBegin), c->numSMs};
-            int grid = c->numSMs * perSM;
-            if (grid > tq.ntiles) grid = tq.ntiles;
-            k_sweep_list_p<Op><<<grid, SPHK_BLOCK, 0, c->stream>>>(d, op, tq);
         }
         else k_sweep_list<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     } else {
@@ -1703,8 +1374,7 @@ extern "C" int sphk_list_stats(sphk_ctx* c, const sphk_scene* s, long long out_h
     if (rc != SPHK_OK) return rc;
     unsigned long long* dev = reinterpret_cast<unsigned long long*>(c->partial);
     SPHK_CUDA_TRY(cudaMemsetAsync(dev, 0, 3 * sizeof(unsigned long long), c->stream));
-    if (c->group == 2 && !c->tile) k_list_stats<<<256, 256, 0, c->stream>>>(c->cnt + c->listBegin / 2, (c->listEnd + 1) / 2 - c->listBegin / 2, d.kmax, dev);
-    else k_list_stats<<<256, 256, 0, c->stream>>>(c->cnt + c->listBegin, c->listEnd - c->listBegin, c->kmax, dev);
+    k_list_stats<<<256, 256, 0, c->stream>>>(c->cnt + c->listBegin, c->listEnd - c->listBegin, c->kmax, dev);
     c->launches++;
     unsigned long long h[3];
     SPHK_CUDA_TRY(cudaMemcpyAsync(h, dev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

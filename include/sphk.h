@@ -86,23 +86,15 @@ enum {
     SPHK_OPT_LIST_SKIN = 5,      /* neighbour-list skin in 1/1000 of the radius (default 0).  With a skin the list
                                     stays valid while sphk_pbd_delta_pos_apply moves particles by less than skin/2
                                     (tracked on the device; beyond that every sweep falls back to the cell walk) */
-    SPHK_OPT_TILE = 9,           /* 1 (default): tile lists.  A tile = 128 consecutive particles; the particles any of them can
-                                    interact with lie in 9 + 9 contiguous windows of the sorted fluid / boundary records
+    SPHK_OPT_TILE = 9            /* 1: tile lists.  A tile = 128 consecutive particles; the particles any of them can interact
+                                    with lie in 9 + 9 contiguous windows of the sorted fluid / boundary records
                                     (CUDAFunctions.cuh:68: z is the fastest cell dimension), which every sweep stages into
-                                    shared memory with cp.async.bulk behind an mbarrier; neighbour lists hold 16-bit indices
-                                    into the staged windows (half the list traffic, no L1 misses on the gathers).
-                                    0: per-particle int32 lists gathered from global memory through L1 */
-    SPHK_OPT_GROUP = 8,          /* particles per thread in the list sweeps, sharing one neighbour list (the union of
-                                    their neighbours; a candidate outside a member's support contributes exactly 0 to it):
-                                    1 = one list per particle, 2 = consecutive pairs (default: fewer gathers per particle) */
-    SPHK_OPT_SCHEDULE = 7,       /* list sweeps: 0 = one thread block per tile of 128 particles, in launch order;
-                                    1 = persistent blocks, each SM works through its own contiguous run of tiles (tiles that
-                                    are neighbours in space run on the same SM back to back: their gathers hit in L1) */
-    SPHK_OPT_LANES_PER_PARTICLE = 4  /* list sweeps: 1 (default) = thread per particle, sums in the reference's
-                                    sequential order; 4 = four lanes share a particle and split its neighbours,
-                                    partial sums combined by warp shuffles (measured slower on B200: the sweeps
-                                    are bound by L1 sectors per gather, which lane cooperation does not reduce;
-                                    DESIGN.md) */
+                                    shared memory with cp.async.bulk behind an mbarrier; neighbour lists hold 16-bit slots of the
+                                    staged windows (half the list traffic, no L1 misses on the gathers).
+                                    0 (default): per-particle int32 lists gathered from global memory through L1 -- measured
+                                    faster on B200 (profiles/r02: 123 vs 175 us for a 16-byte sweep, 194 vs 327 us for a 32-byte
+                                    sweep at 2M particles): random 16-byte shared-memory reads cost what L1 hits cost, and the
+                                    staged tiles cap the occupancy of the velocity sweeps at 4 blocks per SM */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

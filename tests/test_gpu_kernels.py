@@ -249,7 +249,6 @@ def test_tuned_list_builder_equals_simple_cell_walk(pkg, built, O, skin):
     from cpp_fluid_particles_b200 import capi
     sc, s = _system(pkg, "config0", solver="dfsph", jitter=0.004)
     lists = []
-    s.set_option(capi.OPT_GROUP, 1)
     s.set_option(capi.OPT_TILE, 0)
     # generic cell walk; the default builder (candidate windows staged in shared memory by bulk copies); the same from global memory
     for simple, staged in ((1, 0), (0, 1), (0, 0)):
@@ -270,49 +269,16 @@ def test_tuned_list_builder_equals_simple_cell_walk(pkg, built, O, skin):
     s.close()
 
 
-@pytest.mark.parametrize("skin", [0, 150])
-def test_pair_list_is_union_of_member_lists(pkg, built, O, skin):
-    """SPHK_OPT_GROUP = 2: the list of pair k holds exactly N(2k) u N(2k+1) u {2k, 2k+1} (no duplicates), padded with
-    the far-away dummy record; checked against the per-particle lists of the same state."""
-    _torch()
-    from cpp_fluid_particles_b200 import capi
-    sc, s = _system(pkg, "config0", solver="dfsph", jitter=0.004)
-    n, cap = s.fluid.n, s.fluid.pos.shape[0]
-    s.set_option(capi.OPT_GROUP, 1)
-    s.set_use_list(True, skin); s.search_fluid()
-    c1, e1 = s.neighbor_list()
-    c1, e1 = c1.cpu().numpy(), e1.cpu().numpy()              # e1[b, i, q]
-    s.set_option(capi.OPT_GROUP, 2)
-    s.set_use_list(True, skin); s.search_fluid()
-    c2, e2 = s.neighbor_list()
-    c2 = c2.cpu().numpy()
-    stride2 = (cap + 1) // 2
-    e2 = e2.cpu().numpy().reshape(-1)[: (96 * cap // (4 * stride2)) * 4 * stride2].reshape(-1, stride2, 4)
-    dummy = cap + s.boundary.pos.shape[0]
-    rng = np.random.default_rng(0)
-    for k in list(range(8)) + list(rng.integers(0, n // 2, 400)):
-        i0, i1 = 2 * k, min(2 * k + 1, n - 1)
-        want = set()
-        for i in (i0, i1):
-            want |= set(e1[:, i, :].reshape(-1)[: c1[i]].tolist())
-        want |= {i0, i1}
-        got = e2[:, k, :].reshape(-1)[: c2[k]].tolist()
-        assert len(got) == len(set(got)), f"pair {k}: duplicate entries"
-        assert set(got) == want, f"pair {k}"
-        pad = e2[:, k, :].reshape(-1)[c2[k]: ((c2[k] + 3) // 4) * 4]
-        assert (pad == dummy).all()
-    s.close()
-
-
 @pytest.mark.parametrize("solver", ["wcsph", "dfsph", "pbd"])
-def test_pair_lists_reproduce_single_lists(pkg, built, O, solver):
-    """Whole steps with pair lists against per-particle lists: every member's sum is its own sum with exact zeros
-    interleaved, so states agree to rounding (different kernel instantiations: FMA contraction only)."""
+def test_tile_lists_reproduce_global_lists(pkg, built, O, solver):
+    """SPHK_OPT_TILE = 1 (neighbour windows staged in shared memory by bulk copies, 16-bit lists) against the default
+    int32 lists: the same pairs in the same order through another kernel instantiation -> equal up to FMA contraction;
+    tiles whose windows exceed the staging capacity and out-of-grid particles take the exact cell-walk fallback."""
     _torch()
     from cpp_fluid_particles_b200 import capi, engine
     sc = pkg.scene.benchmark_scene("config0", solver)
     a, b = engine.SphkSystem(sc, step0=False), engine.SphkSystem(sc, step0=False)
-    a.set_option(capi.OPT_GROUP, 1); b.set_option(capi.OPT_GROUP, 2)
+    b.set_option(capi.OPT_TILE, 1)
     for k in range(4):
         a.step(); b.step()
         sa, sb = a.state(), b.state()

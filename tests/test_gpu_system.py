@@ -278,3 +278,42 @@ def test_full_size_properties_2m(pkg, built):
     st_pos = s.fluid.pos.cpu().numpy()
     assert np.isfinite(st_pos).all() and st_pos.min() >= 0 and st_pos.max() <= 0.99 * sc.params.space[0] + 1e-6
     s.close()
+
+
+@pytest.mark.parametrize("solver,iters", [("dfsph", 4), ("sph", 0), ("pbd", 4)])
+def test_headless_cli_matches_facade(pkg, built, tmp_path, solver, iters):
+    """the reference application without its window (app/sph_headless.cpp, C++ against the class API only)
+    run as a process -- constructor + 3 frames, particle dump -- against capi.SphApp on the same scene: the same engine
+    behind two independent restatements of main.cpp's call sites, so the dumps must agree bit for bit; also checks the
+    timing line / JSON summary of oneStep() (main.cpp:300-306)."""
+    _gpu()
+    import json
+    import subprocess
+    from util import ROOT
+    from cpp_fluid_particles_b200 import capi
+    cli = os.path.join(ROOT, "cpp-fluid-particles_b200", "sph_headless")
+    assert os.path.exists(cli), "sph_headless is not built"
+    pyname = {"sph": "wcsph"}.get(solver, solver)
+    sc = pkg.scene.benchmark_scene("mini", pyname)
+    box, (nx, ny, nz), origin = pkg.scene._CONFIGS["mini"]
+    prefix = str(tmp_path / "dump")
+    cmd = [cli, "--solver", solver, "--frames", "3", "--box", str(box), "--block", str(nx), str(ny), str(nz),
+           "--origin", *[repr(float(o)) for o in origin], "--dump", prefix, "--quiet"]
+    if iters:
+        cmd += ["--iters", str(iters)]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    summary = json.loads(out.stdout.strip().splitlines()[-1])
+    assert summary["n_fluid"] == sc.fluid.shape[0] and summary["n_boundary"] == sc.boundary.shape[0]
+    assert summary["frames"] == 3 and summary["avg_ms_per_frame"] > 0 and summary["particle_steps_per_s"] > 0
+    app = capi.SphApp(sc)
+    for _ in range(3):
+        app.step()
+    st = app.download()
+    app.close()
+    pos = np.fromfile(prefix + ".pos.f32", np.float32).reshape(-1, 3)
+    den = np.fromfile(prefix + ".density.f32", np.float32)
+    rgb = np.fromfile(prefix + ".rgb.f32", np.float32).reshape(-1, 3)
+    assert np.array_equal(bits(pos), bits(st["pos"])), "CLI and facade drive the same engine through the same call sites"
+    assert np.array_equal(bits(den), bits(st["density"]))
+    assert rgb.shape == pos.shape and np.isfinite(rgb).all() and rgb.min() >= 0.0 and rgb.max() <= 1.0
