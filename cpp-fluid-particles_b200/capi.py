@@ -25,14 +25,14 @@ SPHK_FUNCTIONS = [
     "sphk_dfsph_den_error", "sphk_dfsph_den_correct", "sphk_reduce_abs_sum", "sphk_copy", "sphk_pbd_density_lambda",
     "sphk_pbd_delta_pos_apply", "sphk_pbd_velocity_from_positions", "sphk_pbd_xsph", "sphk_get_permutation",
     "sphk_list_stats", "sphk_set_active_range", "sphk_push_range", "sphk_build_neighbor_list", "sphk_get_neighbor_list", "sphk_fused_density_color_grad",
-    "sphk_fused_dfsph_density_alpha_color_grad", "sphk_fused_dfsph_density_alpha_div_error", "sphk_fused_viscosity_surface", "sphk_export_dots", "sphk_particles_advect", "sphk_add_launches",
+    "sphk_fused_dfsph_density_alpha_color_grad", "sphk_fused_dfsph_density_alpha_div_error", "sphk_loop_begin", "sphk_loop_next", "sphk_loop_end", "sphk_loop_iterations", "sphk_fused_viscosity_surface", "sphk_export_dots", "sphk_particles_advect", "sphk_add_launches",
     "sphk_mg_unique_id", "sphk_mg_init", "sphk_mg_destroy", "sphk_mg_ipc_handle", "sphk_mg_ipc_connect", "sphk_mg_set_transport",
     "sphk_mg_exchange_ints", "sphk_mg_allreduce_sum", "sphk_mg_exchange_slices", "sphk_mg_halo", "sphk_mg_check", "sphk_mg_stats",
 ]
 SPH_APP_FUNCTIONS = [
     "sph_app_create", "sph_app_destroy", "sph_app_step", "sph_app_fluid_size", "sph_app_boundary_size",
     "sph_app_download_fluid", "sph_app_download_boundary", "sph_app_upload_fluid", "sph_app_engine",
-    "sph_app_submit", "sph_app_wait",
+    "sph_app_submit", "sph_app_wait", "sph_app_dfsph_iterations", "sph_app_set_option",
 ]
 
 OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_LIST_SKIN, OPT_SIMPLE_LIST_BUILD, OPT_TILE, OPT_STAGED_LIST_BUILD = 1, 2, 5, 6, 9, 10
@@ -188,6 +188,18 @@ class SphApp:
     def wait(self):
         if self.L.sph_app_wait(self.h):
             raise RuntimeError("sph_app_wait failed")
+
+    def dfsph_iterations(self):
+        """(divergence, density) iteration counts of the last DFSPH step."""
+        a, b = C.c_int(0), C.c_int(0)
+        if self.L.sph_app_dfsph_iterations(self.h, C.byref(a), C.byref(b)):
+            raise RuntimeError("sph_app_dfsph_iterations: not a DFSPH system of this engine")
+        return int(a.value), int(b.value)
+
+    def set_option(self, option: int, value: int):
+        """1: device-side loop tests (adaptive DFSPH), 2: fused sweeps, 3: step graph."""
+        if self.L.sph_app_set_option(self.h, C.c_int(option), C.c_int(value)):
+            raise RuntimeError("sph_app_set_option failed")
 
     def close(self):
         if getattr(self, "h", None):

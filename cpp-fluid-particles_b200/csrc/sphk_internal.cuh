@@ -39,6 +39,18 @@ struct KConst {
     float r2cut;  // R^2 (1 + 1e-5): candidates beyond contribute exactly 0
 };
 
+// Device-side iteration control of one adaptive solver loop (DFSPH divergence / density correction): the loop test of
+// DFSPHSolver.cu:187,347 evaluated on the device, so that the host enqueues a fixed sequence of launches (max_iter
+// iterations, the ones after convergence return at once) instead of reading an error sum back every iteration.
+struct LoopState {
+    int active;        // the loop condition; kernels of the loop body return immediately when it is 0
+    int iters;         // iterations executed
+    int minIter, maxIter, reduceFrom;
+    float threshold;   // errorThreshold * num * rho0
+    float total;       // last error sum (FLT_MAX before the first reduction)
+    int pad;
+};
+
 struct sphk_ctx {
     cudaStream_t stream = nullptr;
     int capF = 0, capB = 0;          // capacities; boundary lives at unified index capF + b
@@ -56,6 +68,8 @@ struct sphk_ctx {
     float* massRange = nullptr;                  // [2] device: min / max fluid mass of the last search (as float bits)
     float* tmpF = nullptr;                       // [3*capF] permute temp
     float* partial = nullptr;                    // [1024] reduction partials
+    LoopState* loops = nullptr;                  // [2] device-side loop control (sphk_loop_*)
+    const int* pred = nullptr;                   // non-null: sweeps / reductions run only while *pred != 0
     int* nbr = nullptr;                          // [kmax * capF] neighbour list, nbr[k*capF + i]
     int* cnt = nullptr;                          // [capF] true neighbour count (may exceed kmax)
     float* pinned = nullptr;                     // host pinned scalar
@@ -95,6 +109,7 @@ struct DevScene {
     float4* posBuild;                // positions at list build (skin lists)
     int nF, bOff, nbrStride, kmax;
     const int2* tileWin;             // tile lists: the 18 windows of every tile (written by the list builder)
+    const int* pred;                 // non-null: the kernel returns at once when *pred == 0 (device-controlled solver loops)
     int dummy;                       // index of a record far away from everything with zero mass: list padding that
                                      // contributes exactly 0 to every particle (group lists cannot pad with "self")
     int iBegin, iEnd;                // sweeps compute particles [iBegin, iEnd)

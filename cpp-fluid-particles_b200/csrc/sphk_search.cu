@@ -200,6 +200,7 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
     if (e == cudaSuccess) e = dalloc(&c->dispMax, 1);
     if (e == cudaSuccess) e = dalloc(&c->tmpF, 3 * static_cast<size_t>(max_fluid));
     if (e == cudaSuccess) e = dalloc(&c->partial, 1024);
+    if (e == cudaSuccess) e = dalloc(&c->loops, 2);
     if (e == cudaSuccess) e = dalloc(&c->cnt, static_cast<size_t>(max_fluid));
     if (e == cudaSuccess) e = dalloc(&c->tileWin, (static_cast<size_t>(max_fluid) / SPHK_BLOCK + 1) * SPHK_TILE_WINS);
     if (e == cudaSuccess) {
@@ -225,7 +226,7 @@ extern "C" void sphk_destroy(sphk_ctx* c) {
     if (!c) return;
     cudaFree(c->keys); cudaFree(c->keysSorted); cudaFree(c->idx); cudaFree(c->idxSorted);
     cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec.a); cudaFree(c->rec.b); cudaFree(c->massRange); cudaFree(c->dispMax);
-    cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp); cudaFree(c->tileWin);
+    cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->loops); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp); cudaFree(c->tileWin);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
 }
@@ -389,6 +390,91 @@ extern "C" int sphk_reduce_abs_sum(sphk_ctx* c, const float* x, int n, float* ho
     SPHK_CUDA_TRY(cudaMemcpyAsync(c->pinned, c->partial, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     SPHK_CUDA_TRY(cudaStreamSynchronize(c->stream));
     *host_out = *c->pinned;
+    return SPHK_OK;
+}
+
+// ---- device-side loop control (adaptive DFSPH, DFSPHSolver.cu:187,205-207,347,360) ----------------------------------
+__global__ void k_loop_begin(LoopState* st, int minIter, int maxIter, float threshold, int reduceFrom) {
+    st->iters = 0; st->minIter = minIter; st->maxIter = maxIter; st->reduceFrom = reduceFrom;
+    st->threshold = threshold; st->total = 3.402823466e38f;
+    st->active = ((0 < minIter) || (st->total > threshold)) && (0 < maxIter) ? 1 : 0;
+}
+// first stage of the error sum of iteration iters + 1 (same fixed-shape tree as sphk_reduce_abs_sum: same sum, bit for bit)
+__global__ void __launch_bounds__(256) k_loop_partial(const LoopState* st, const float* __restrict__ x, int n, float* __restrict__ partial) {
+    if (!st->active || st->iters + 1 < st->reduceFrom) return;
+    __shared__ float sm[8];
+    float s = 0.f;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) s += fabsf(x[i]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        s = sm[threadIdx.x];
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+// second stage + the loop test: ++iter; total = sum (from iteration reduceFrom on); active = (iter < min || total > thr) && iter < max
+__global__ void __launch_bounds__(256) k_loop_finish(LoopState* st, const float* __restrict__ partial, int m) {
+    if (!st->active) return;
+    __shared__ float sm[8];
+    const int iters = st->iters + 1;
+    float total = st->total;
+    if (iters >= st->reduceFrom) {
+        float s = 0.f;
+        for (int i = threadIdx.x; i < m; i += 256) s += partial[i];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            s = sm[threadIdx.x];
+            for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+            if (threadIdx.x == 0) sm[0] = s;
+        }
+        __syncthreads();
+        total = sm[0];
+    }
+    if (threadIdx.x == 0) {
+        st->iters = iters;
+        st->total = total;
+        st->active = ((iters < st->minIter) || (total > st->threshold)) && (iters < st->maxIter) ? 1 : 0;
+    }
+}
+
+extern "C" int sphk_loop_begin(sphk_ctx* c, int slot, int min_iter, int max_iter, float threshold, int reduce_from_iter) {
+    if (!c || slot < 0 || slot > 1 || max_iter < 0) return SPHK_ERR_INVALID;
+    k_loop_begin<<<1, 1, 0, c->stream>>>(c->loops + slot, min_iter, max_iter, threshold, reduce_from_iter);
+    c->launches++;
+    c->pred = &c->loops[slot].active;
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+extern "C" int sphk_loop_next(sphk_ctx* c, int slot, const float* error, int n) {
+    if (!c || slot < 0 || slot > 1 || !error || n < 0) return SPHK_ERR_INVALID;
+    int blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1024) blocks = 1024;
+    k_loop_partial<<<blocks, 256, 0, c->stream>>>(c->loops + slot, error, n, c->partial);
+    k_loop_finish<<<1, 256, 0, c->stream>>>(c->loops + slot, c->partial, blocks);
+    c->launches += 2;
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+extern "C" int sphk_loop_end(sphk_ctx* c, int slot) {
+    if (!c || slot < 0 || slot > 1) return SPHK_ERR_INVALID;
+    c->pred = nullptr;
+    return SPHK_OK;
+}
+
+extern "C" int sphk_loop_iterations(sphk_ctx* c, int slot, int* iterations_host, float* last_total_host) {
+    if (!c || slot < 0 || slot > 1 || !iterations_host) return SPHK_ERR_INVALID;
+    LoopState h;
+    SPHK_CUDA_TRY(cudaMemcpyAsync(&h, c->loops + slot, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    SPHK_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *iterations_host = h.iters;
+    if (last_total_host) *last_total_host = h.total;
     return SPHK_OK;
 }
 

@@ -368,6 +368,7 @@ __device__ __forceinline__ void walk_cells(const DevScene& s, const Op& op, type
 
 template <class Op>
 __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_cells(const DevScene s, const Op op) {
+    if (s.pred && *s.pred == 0) return;
     const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= s.iEnd) return;
     float4 lo, hi;
@@ -422,6 +423,7 @@ __device__ __forceinline__ void sweep_list_particle(const DevScene& s, const Op&
 
 template <class Op>
 __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, const Op op) {
+    if (s.pred && *s.pred == 0) return;
     const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= s.iEnd) return;
     sweep_list_particle(s, op, i);
@@ -686,6 +688,7 @@ __device__ __forceinline__ void tile_pair(const DevScene& s, const Op& op, typen
 template <class Op>
 __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_tile(const DevScene s, const Op op) {
     extern __shared__ float4 sm[];                  // A[SPHK_TILE_CAP + 1], then B[SPHK_TILE_CAP + 1] for velocity sweeps
+    if (s.pred && *s.pred == 0) return;
     float4* smA = sm;
     float4* smB = sm + (SPHK_TILE_CAP + 1);
     __shared__ unsigned long long bar;
@@ -962,6 +965,7 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
     d.nbrStride = c->capF; d.kmax = c->kmax;
     d.dummy = c->capF + c->capB;
     d.tileWin = c->tileWin;
+    d.pred = c->pred;
     d.cs = c->cs; d.org = c->org; d.cellLength = c->cellLength;
     d.iBegin = c->actCount < 0 ? 0 : c->actBegin;
     d.iEnd = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;

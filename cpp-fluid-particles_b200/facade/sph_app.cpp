@@ -36,6 +36,7 @@ struct sph_batch {
 
 struct sph_app {
     std::shared_ptr<SPHSystem> system;
+    BaseSolver* solver = nullptr;            // owned by `system` (its constructor moves the caller's shared_ptr)
     // pipelined path (created on first sph_app_submit)
     cudaStream_t copyStream = nullptr;
     sph_batch batch[2];
@@ -83,6 +84,7 @@ extern "C" sph_app* sph_app_create(const float* fluid_xyz, int n_fluid,
         break;
     }
     auto* app = new sph_app;
+    app->solver = pSolver.get();
     app->system = std::make_shared<SPHSystem>(
         fluidParticles, boundaryParticles, pSolver,
         make_float3(p->space[0], p->space[1], p->space[2]), p->cell_length, p->radius, p->dt, p->m0,
@@ -221,6 +223,34 @@ extern "C" int sph_app_wait(sph_app* app) {
     bad |= pipe_run(app, last);
     bad |= cudaStreamSynchronize(app->copyStream) != cudaSuccess;
     return bad;
+}
+
+// ---- introspection of this repository's engine (absent from the reference build of the facade) -------------------------
+extern "C" int sph_app_dfsph_iterations(sph_app* app, int* divergence_iters, int* density_iters) {
+#ifdef SPH_APP_REFERENCE_ENGINE
+    (void)app; (void)divergence_iters; (void)density_iters;
+    return 1;
+#else
+    auto* d = dynamic_cast<DFSPHSolver*>(app->solver);
+    if (!d) return 1;
+    if (divergence_iters) *divergence_iters = d->lastDivergenceIterations();
+    if (density_iters) *density_iters = d->lastDensityIterations();
+    return 0;
+#endif
+}
+
+extern "C" int sph_app_set_option(sph_app* app, int option, int value) {
+#ifdef SPH_APP_REFERENCE_ENGINE
+    (void)app; (void)option; (void)value;
+    return 1;
+#else
+    switch (option) {
+    case 1: { auto* d = dynamic_cast<DFSPHSolver*>(app->solver); if (!d) return 1; d->setDeviceLoops(value != 0); return 0; }
+    case 2: { auto* b = dynamic_cast<BasicSPHSolver*>(app->solver); if (!b) return 1; b->setFusedSweeps(value != 0); return 0; }
+    case 3: app->system->setStepGraph(value != 0); return 0;
+    default: return 1;
+    }
+#endif
 }
 
 extern "C" const char* sph_app_engine(void) {

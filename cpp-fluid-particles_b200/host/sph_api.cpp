@@ -210,6 +210,18 @@ int DFSPHSolver::correctDivergenceError(float rho0, float dt, float errorThresho
     if (!firstErrorDone)
         check(sphk_dfsph_div_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0),
               "sphk_dfsph_div_error");
+    if (errorThreshold >= 0.0f && deviceLoops_) {
+        // the loop test runs on the device: maxIter bodies are enqueued, the ones after convergence return at once
+        check(sphk_loop_begin(ctx, 0, 1, maxIter_, errorThreshold * num * rho0, 1), "sphk_loop_begin");
+        for (int k = 0; k < maxIter_; ++k) {
+            check(sphk_dfsph_div_correct(ctx, &current_.abi, bufferFloat.addr()), "sphk_dfsph_div_correct");
+            check(sphk_dfsph_div_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0),
+                  "sphk_dfsph_div_error");
+            check(sphk_loop_next(ctx, 0, error.addr(), num), "sphk_loop_next");
+        }
+        check(sphk_loop_end(ctx, 0), "sphk_loop_end");
+        return -1;      // known on the device; lastDivergenceIterations() reads it back
+    }
     while ((iter < 1 || totalError > errorThreshold * num * rho0) && iter < maxIter_) {
         check(sphk_dfsph_div_correct(ctx, &current_.abi, bufferFloat.addr()), "sphk_dfsph_div_correct");
         check(sphk_dfsph_div_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0),
@@ -235,6 +247,18 @@ int DFSPHSolver::project(std::shared_ptr<SPHParticles>& fluids, const std::share
     check(sphk_dfsph_den_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0, nullptr),
           "sphk_dfsph_den_error");
     check(sphk_copy(ctx, denWarmStiff.addr(), bufferFloat.addr(), num), "sphk_copy");     // :185
+    if (errorThreshold >= 0.0f && deviceLoops_) {
+        check(sphk_loop_begin(ctx, 1, 2, maxIter_, errorThreshold * num * rho0, 2), "sphk_loop_begin");
+        for (int k = 0; k < maxIter_; ++k) {
+            check(sphk_dfsph_den_correct(ctx, &current_.abi, bufferFloat.addr(), dt), "sphk_dfsph_den_correct");
+            check(sphk_dfsph_den_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0,
+                                       denWarmStiff.addr()),
+                  "sphk_dfsph_den_error");                                                // + :199-203 fused
+            check(sphk_loop_next(ctx, 1, error.addr(), num), "sphk_loop_next");
+        }
+        check(sphk_loop_end(ctx, 1), "sphk_loop_end");
+        return -1;
+    }
     while ((iter < 2 || totalError > errorThreshold * num * rho0) && iter < maxIter_) {
         check(sphk_dfsph_den_correct(ctx, &current_.abi, bufferFloat.addr(), dt), "sphk_dfsph_den_correct");
         check(sphk_dfsph_den_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0,
@@ -245,6 +269,13 @@ int DFSPHSolver::project(std::shared_ptr<SPHParticles>& fluids, const std::share
             check(sphk_reduce_abs_sum(ctx, error.addr(), num, &totalError), "sphk_reduce_abs_sum");
     }
     return iter;
+}
+
+int DFSPHSolver::loopIterations(int slot, int hostCount) const {
+    if (hostCount >= 0 || !current_.ctx) return hostCount;
+    int it = 0;
+    check(sphk_loop_iterations(current_.ctx, slot, &it, nullptr), "sphk_loop_iterations");
+    return it;
 }
 
 // ================================================================================================

@@ -223,9 +223,13 @@ public:
                       const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
                       int3 cellSize, float cellLength, float radius, float dt, float rho0, float rhoB, float stiff,
                       float visc, float3 G, float surfaceTensionIntensity, float airPressure) override;
-    bool stepIsGraphSafe() const override { return densityErrorThreshold < 0.0f && divergenceErrorThreshold < 0.0f; }
-    int lastDivergenceIterations() const { return itDiv_; }   // addition: iteration counts of the last step
-    int lastDensityIterations() const { return itDen_; }
+    // fixed iteration counts (negative thresholds, Q11), or loop tests evaluated on the device: either way the step is a
+    // fixed launch sequence without host synchronisation
+    bool stepIsGraphSafe() const override { return deviceLoops_ || (densityErrorThreshold < 0.0f && divergenceErrorThreshold < 0.0f); }
+    // addition: false = the reference's host loop (one error sum read back per iteration, DFSPHSolver.cu:206,360)
+    void setDeviceLoops(bool on) { if (on != deviceLoops_) ++configEpoch_; deviceLoops_ = on; }
+    int lastDivergenceIterations() const { return loopIterations(0, itDiv_); }   // addition: iteration counts of the last step
+    int lastDensityIterations() const { return loopIterations(1, itDen_); }
 protected:
     // density-error correction with warm start (DFSPHSolver.cu:160-210); hides BasicSPHSolver::project
     virtual int project(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
@@ -241,7 +245,9 @@ private:
     const float densityErrorThreshold;
     const float divergenceErrorThreshold;
     const int maxIter;
-    int itDiv_ = 0, itDen_ = 0;
+    int itDiv_ = 0, itDen_ = 0;      // -1: the count lives on the device (read back on demand)
+    bool deviceLoops_ = true;
+    int loopIterations(int slot, int hostCount) const;
 };
 
 // ---- PBDSolver.h:20-85 ------------------------------------------------------------------------

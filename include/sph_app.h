@@ -66,6 +66,11 @@ int   sph_app_submit(sph_app* app, const float* pos_in_xyz, const float* vel_in_
                      float* pos_out_xyz, float* vel_out_xyz, float* density_out);
 /* Steps every submitted batch that has not run yet and waits for all downloads. */
 int   sph_app_wait(sph_app* app);
+/* Introspection / switches of this repository's engine (return 1 on the reference build of the facade):
+ * iteration counts of the last DFSPH step; option 1 = device-side loop tests for adaptive DFSPH (default on; 0 = the
+ * reference's host loop with one error sum read back per iteration), 2 = fused sweeps (default on), 3 = step graph. */
+int   sph_app_dfsph_iterations(sph_app* app, int* divergence_iters, int* density_iters);
+int   sph_app_set_option(sph_app* app, int option, int value);
 /* Name of the engine underneath: "reference-cuda" or "b200-native". */
 const char* sph_app_engine(void);
 

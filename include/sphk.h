@@ -193,6 +193,18 @@ int sphk_dfsph_den_error(sphk_ctx* ctx, const sphk_scene* s, const float* alpha,
 int sphk_dfsph_den_correct(sphk_ctx* ctx, const sphk_scene* s, const float* stiff, float dt);
 /* thrust::reduce(error, abs_plus), DFSPHSolver.cu:206,360.  Synchronises; result to *host_out. */
 int sphk_reduce_abs_sum(sphk_ctx* ctx, const float* x, int n, float* host_out);
+/* Device-side control of an adaptive solver loop: the loop tests of DFSPHSolver.cu:187 / :347
+ *     while ((iter < min_iter || totalError > threshold) && iter < max_iter) { body; ++iter; [totalError = reduce] }
+ * evaluated on the device.  The host enqueues max_iter bodies; between sphk_loop_begin and sphk_loop_end every sweep
+ * returns at once when the loop has ended, so no error sum travels to the host and the launch sequence is fixed (a
+ * CUDA graph can replay it).  sphk_loop_next ends one iteration: ++iter, totalError = sum |error| (the same fixed-shape
+ * reduction as sphk_reduce_abs_sum) from iteration reduce_from_iter on (DFSPHSolver.cu:205: the density loop reduces
+ * from its second iteration), then the loop test.  slot: 0 or 1.  threshold = errorThreshold * num * rho0. */
+int sphk_loop_begin(sphk_ctx* ctx, int slot, int min_iter, int max_iter, float threshold, int reduce_from_iter);
+int sphk_loop_next(sphk_ctx* ctx, int slot, const float* error, int n);
+int sphk_loop_end(sphk_ctx* ctx, int slot);
+/* iterations the loop executed and its last error sum (synchronises) */
+int sphk_loop_iterations(sphk_ctx* ctx, int slot, int* iterations_host, float* last_total_host);
 /* cudaMemcpy D2D of a float array, DFSPHSolver.cu:185 */
 int sphk_copy(sphk_ctx* ctx, float* dst, const float* src, int n_floats);
 
