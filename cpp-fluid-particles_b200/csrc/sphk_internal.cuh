@@ -76,6 +76,10 @@ struct sphk_ctx {
     // ---- state ----
     int nF = 0, nB = 0;
     int actBegin = 0, actCount = -1; // active (owned) range of the sweeps; -1: all
+    const int* rangeDev = nullptr;   // non-null: the active range {begin, count} lives in DEVICE memory (slab ranks: computed from
+                                     // the cell ranges by sphk_mg_plane_ranges, never read by the host); kernels are launched over
+                                     // all nF particles and the ones outside the range return
+    const int* listRangeDev = nullptr;
     int kmax = 96;
     bool useList = true;
     bool stagedBuild = true;         // build the list from candidate windows staged in shared memory by bulk copies (default);
@@ -113,11 +117,17 @@ struct DevScene {
     int dummy;                       // index of a record far away from everything with zero mass: list padding that
                                      // contributes exactly 0 to every particle (group lists cannot pad with "self")
     int iBegin, iEnd;                // sweeps compute particles [iBegin, iEnd)
+    const int* rangeDev;             // non-null: ... intersected with the device-resident range {begin, count}
     int3 cs, org;
     float cellLength;
     float r2list;                    // candidate cut-off of the cell walk: r2cut, or (R + skin)^2 when building a skin list
     KConst k;
 };
+
+__device__ __forceinline__ bool in_range(const DevScene& s, int i) {
+    if (s.rangeDev) { const int b = s.rangeDev[0]; return i >= b && i < b + s.rangeDev[1]; }
+    return i >= s.iBegin && i < s.iEnd;
+}
 
 // ---- tiny float3 algebra (component-wise, left to right) ---------------------------------------
 __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }

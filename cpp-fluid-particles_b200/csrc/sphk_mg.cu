@@ -162,6 +162,10 @@ struct HaloArgs {
     const float4* posBuild;  // skin tracking (PBD position halos), or nullptr
     unsigned int* dispMax;
     unsigned long long timeoutNs;
+    const int* rangesDev;    // non-null: the eight plane ranges live in device memory (sphk_mg_plane_ranges); the kernel
+                             // derives the slices to send and the ghost ranges from them, side[].src/ghost* hold only the
+                             // "has a neighbour" information
+    unsigned int capFloats;  // mailbox payload capacity (device-side check in rangesDev mode)
 };
 
 constexpr int kHaloBlock = 256;
@@ -172,6 +176,18 @@ constexpr int kHaloBlock = 256;
 __global__ void __launch_bounds__(kHaloBlock) k_halo_mailbox(HaloArgs a) {
     const int nthreads = gridDim.x * kHaloBlock;
     const int tid = blockIdx.x * kHaloBlock + threadIdx.x;
+    if (a.rangesDev) {       // ranges = {first_begin, first_count, last_begin, last_count, ghostL_begin, ghostL_count, ghostR_begin, ghostR_count}
+        const int* r = a.rangesDev;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (a.side[s].peerBox) {
+                const int n = r[2 * s + 1] * a.width;
+                a.side[s].src = a.array + static_cast<size_t>(r[2 * s]) * a.width;
+                a.side[s].sendFloats = static_cast<unsigned int>(n) > a.capFloats ? -1 : n;
+            }
+            if (a.side[s].myBox) { a.side[s].ghostBegin = r[4 + 2 * s]; a.side[s].ghostCount = r[5 + 2 * s]; }
+        }
+    }
     // ---- 1. remote stores -------------------------------------------------------------------------------------
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -460,8 +476,27 @@ extern "C" int sphk_mg_exchange_slices(sphk_mg_comm* m, int narrays, const float
 // ranges = {first_begin, first_count, last_begin, last_count, ghostL_begin, ghostL_count, ghostR_begin, ghostR_count}
 // what: sphk_push_range mask (1 vel: array = scene->fluid.vel, width 3; 2 scalar: width 1; 4 pos: array =
 // scene->fluid.pos, width 3) or 0 for an array no record mirrors (colour gradient, density, pressure).
+static int halo_impl(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, int what, float* array, int width, const int ranges[8],
+                     const int* rangesDev, int maxParticles);
+
 extern "C" int sphk_mg_halo(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, int what, float* array, int width, const int ranges[8]) {
-    if (!m || !c || !s || !array || !ranges || (width != 1 && width != 3) || (what != 0 && what != 1 && what != 2 && what != 4))
+    if (!ranges) return SPHK_ERR_INVALID;
+    return halo_impl(m, c, s, what, array, width, ranges, nullptr, 0);
+}
+
+/* the same with the eight plane ranges in DEVICE memory (written by sphk_mg_plane_ranges; the host never reads them):
+ * mailbox transport only.  max_particles bounds the size of a plane (grid sizing). */
+extern "C" int sphk_mg_halo_device(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, int what, float* array, int width,
+                                   const int* device_ranges8, int max_particles) {
+    if (!device_ranges8 || max_particles < 0) return SPHK_ERR_INVALID;
+    if (!m || m->transport != 1) return SPHK_ERR_STATE;
+    static const int zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    return halo_impl(m, c, s, what, array, width, zero, device_ranges8, max_particles);
+}
+
+static int halo_impl(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, int what, float* array, int width, const int ranges[8],
+                     const int* rangesDev, int maxParticles) {
+    if (!m || !c || !s || !array || (width != 1 && width != 3) || (what != 0 && what != 1 && what != 2 && what != 4))
         return SPHK_ERR_INVALID;
     if ((what == 2 && width != 1) || ((what == 1 || what == 4) && width != 3)) return SPHK_ERR_INVALID;
     for (int k = 0; k < 4; ++k)
@@ -521,9 +556,12 @@ extern "C" int sphk_mg_halo(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, i
     a.posBuild = track ? c->snapA : nullptr;
     a.dispMax = c->dispMax;
     a.timeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+    a.rangesDev = rangesDev;
+    a.capFloats = static_cast<unsigned int>(m->capFloats);
     int work = ranges[1] > ranges[3] ? ranges[1] : ranges[3];
     if (ranges[5] > work) work = ranges[5];
     if (ranges[7] > work) work = ranges[7];
+    if (rangesDev) work = maxParticles;
     int blocks = (work * width / 4 + kHaloBlock - 1) / kHaloBlock;
     if (blocks < 1) blocks = 1;
     if (blocks > sm_count()) blocks = sm_count();
@@ -532,6 +570,73 @@ extern "C" int sphk_mg_halo(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, i
     if (what & 4) c->posDirty = true;
     SPHK_CUDA_TRY(cudaGetLastError());
     return tooBig ? SPHK_ERR_CAPACITY : SPHK_OK;
+}
+
+// ---- host-free step bookkeeping -----------------------------------------------------------------------------------------
+// Everything a slab rank derives from the cell ranges of its freshly sorted set, computed where the data is:
+//   out[0..7]   plane offsets s0, s1, s2, s3, s_{w-1}, s_w, s_{w+1}, s_end (slabs.plane_ranges)
+//   out[8..15]  halo ranges {first_begin, first_count, last_begin, last_count, ghostL_begin, ghostL_count, ghostR_begin, ghostR_count}
+//   out[16..17] active (owned) range {begin, count}                                     -> sphk_set_active_range_device
+//   out[18..21] next step's candidates {to_left_begin, to_left_count, to_right_begin, to_right_count}
+//   out[22..23] what each neighbour has to know: {to_left_count, to_right_count}         -> sphk_mg_exchange_ints_async
+__global__ void k_plane_ranges(const int* __restrict__ cs, int planeCells, int w, int* __restrict__ out) {
+    const int s0 = cs[0], s1 = cs[planeCells], s2 = cs[2 * planeCells], s3 = cs[3 * planeCells];
+    const int swm1 = cs[(w - 1 > 0 ? w - 1 : 0) * planeCells], sw = cs[w * planeCells], sw1 = cs[(w + 1) * planeCells],
+              send = cs[(w + 2) * planeCells];
+    out[0] = s0; out[1] = s1; out[2] = s2; out[3] = s3; out[4] = swm1; out[5] = sw; out[6] = sw1; out[7] = send;
+    const int fb = s1, fe = (w >= 2) ? s2 : sw1;           // first owned plane
+    const int lb = (w >= 2) ? sw : s1, le = sw1;           // last owned plane
+    out[8] = fb; out[9] = fe - fb; out[10] = lb; out[11] = le - lb;
+    out[12] = s0; out[13] = s1 - s0; out[14] = sw1; out[15] = send - sw1;
+    out[16] = s1; out[17] = sw1 - s1;
+    const int tlb = s1, tle = (w >= 2) ? (s3 < sw1 ? s3 : sw1) : sw1;
+    const int trb = (w >= 2) ? (swm1 > s1 ? swm1 : s1) : s1, tre = sw1;
+    out[18] = tlb; out[19] = tle - tlb; out[20] = trb; out[21] = tre - trb;
+    out[22] = tle - tlb; out[23] = tre - trb;
+}
+
+extern "C" int sphk_mg_plane_ranges(sphk_mg_comm* m, const int* cell_start_fluid, int plane_cells, int w, int* device_out24,
+                                    int* pinned_host_out24) {
+    if (!m || !cell_start_fluid || plane_cells <= 0 || w < 1 || !device_out24) return SPHK_ERR_INVALID;
+    k_plane_ranges<<<1, 1, 0, m->stream>>>(cell_start_fluid, plane_cells, w, device_out24);
+    if (pinned_host_out24)
+        SPHK_CUDA_TRY(cudaMemcpyAsync(pinned_host_out24, device_out24, 24 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+/* `count` ints to each neighbour and back, all on the stream and WITHOUT a host synchronisation: the values to send are
+ * read from device memory, the received ones land in pinned host memory once the stream reaches the copy (record an event
+ * after this call and wait for it before reading them).  A missing neighbour yields zeros. */
+extern "C" int sphk_mg_exchange_ints_async(sphk_mg_comm* m, const int* device_to_left, const int* device_to_right, int count,
+                                           int* pinned_from_left, int* pinned_from_right) {
+    if (!m || count < 1 || count > SPHK_MG_MAX_INTS || !device_to_left || !device_to_right || !pinned_from_left || !pinned_from_right)
+        return SPHK_ERR_INVALID;
+    NcclApi& n = nccl();
+    const int K = SPHK_MG_MAX_INTS;
+    SPHK_CUDA_TRY(cudaMemsetAsync(m->dInts + 2 * K, 0, 2 * K * sizeof(int), m->stream));
+    SPHK_NCCL_TRY(n.GroupStart());
+    if (m->rank > 0) {
+        SPHK_NCCL_TRY_IN_GROUP(n.Send(device_to_left, count, kNcclInt32, m->rank - 1, m->comm, m->stream));
+        SPHK_NCCL_TRY_IN_GROUP(n.Recv(m->dInts + 2 * K, count, kNcclInt32, m->rank - 1, m->comm, m->stream));
+    }
+    if (m->rank < m->world - 1) {
+        SPHK_NCCL_TRY_IN_GROUP(n.Send(device_to_right, count, kNcclInt32, m->rank + 1, m->comm, m->stream));
+        SPHK_NCCL_TRY_IN_GROUP(n.Recv(m->dInts + 3 * K, count, kNcclInt32, m->rank + 1, m->comm, m->stream));
+    }
+    SPHK_NCCL_TRY(n.GroupEnd());
+    SPHK_CUDA_TRY(cudaMemcpyAsync(pinned_from_left, m->dInts + 2 * K, count * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    SPHK_CUDA_TRY(cudaMemcpyAsync(pinned_from_right, m->dInts + 3 * K, count * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    return SPHK_OK;
+}
+
+/* the mailbox error word into pinned host memory, no synchronisation (see sphk_mg_check for the bits) */
+extern "C" int sphk_mg_check_async(sphk_mg_comm* m, int* pinned_error_bits) {
+    if (!m || !pinned_error_bits) return SPHK_ERR_INVALID;
+    if (!m->mail) { *pinned_error_bits = 0; return SPHK_OK; }
+    MailTail* tail = reinterpret_cast<MailTail*>(m->mail + flags_offset(m));
+    SPHK_CUDA_TRY(cudaMemcpyAsync(pinned_error_bits, &tail->error, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    return SPHK_OK;
 }
 
 /* Reads the mailbox error word (synchronises the stream): 0 = fine; bit 0/1: timed out waiting for the left/right

@@ -370,7 +370,7 @@ template <class Op>
 __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_cells(const DevScene s, const Op op) {
     if (s.pred && *s.pred == 0) return;
     const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= s.iEnd) return;
+    if (!in_range(s, i)) return;
     float4 lo, hi;
     rec_full(s.rec + i, lo, hi);
     typename Op::Acc acc;
@@ -425,7 +425,7 @@ template <class Op>
 __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, const Op op) {
     if (s.pred && *s.pred == 0) return;
     const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= s.iEnd) return;
+    if (!in_range(s, i)) return;
     sweep_list_particle(s, op, i);
 }
 
@@ -561,7 +561,7 @@ k_build_tile(const DevScene s, unsigned short* __restrict__ nbr16, int* __restri
     const int T = sPre[SPHK_TILE_WINS];
     const bool staged = T <= SPHK_TILE_CAP;
     if (staged && T > 0) mbar_wait(&bar, 0);        // every thread: the block must not retire with bulk copies in flight
-    if (!have || i < s.iBegin || i >= s.iEnd) return;
+    if (!have || !in_range(s, i)) return;
     if (posBuild) posBuild[i] = lo;
     if (!staged || c >= ncells) { cnt[i] = s.kmax + 1; return; }      // this particle walks the cells (exact fallback)
     const float3 xi = xyz(lo);
@@ -646,7 +646,7 @@ k_build_list_staged(const DevScene s, int* __restrict__ nbr, int* __restrict__ c
     const int T = sPre[SPHK_TILE_WINS];
     const bool staged = T <= SPHK_BUILD_CAP;
     if (staged && T > 0) mbar_wait(&bar, 0);        // every thread: the block must not retire with bulk copies in flight
-    if (!have || i < s.iBegin || i >= s.iEnd) return;
+    if (!have || !in_range(s, i)) return;
     if (!staged || c >= ncells) { build_particle_global(s, i, lo, nbr, cnt, posBuild); return; }
     const float3 xi = xyz(lo);
     const int zlo = max(cz - 1, 0), zhi = min(cz + 1, s.cs.z - 1);
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_tile(const DevScene s, con
     __shared__ int sPre[SPHK_TILE_WINS + 1];
     const int tile = s.iBegin / SPHK_BLOCK + blockIdx.x;
     const int i = tile * SPHK_BLOCK + threadIdx.x;
-    const bool on = i >= s.iBegin && i < s.iEnd;
+    const bool on = in_range(s, i);
     if (threadIdx.x < SPHK_TILE_WINS) sWin[threadIdx.x] = s.tileWin[static_cast<size_t>(tile) * SPHK_TILE_WINS + threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) tile_stage(s, sWin, sPre, smA, smB, Op::kHi, &bar);
@@ -802,7 +802,7 @@ __device__ __forceinline__ void build_particle_global(const DevScene& s, int i, 
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_build_list(const DevScene s, int* __restrict__ nbr, int* __restrict__ cnt, float4* __restrict__ posBuild) {
     const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
-    if (i >= s.iEnd) return;
+    if (!in_range(s, i)) return;
     build_particle_global(s, i, rec_lo(s.rec + i), nbr, cnt, posBuild);
 }
 
@@ -912,9 +912,10 @@ k_vel_from_pos(Rec rec, const float* __restrict__ posLast, float* __restrict__ v
     rec_set_vel(rec + i, v); store3(vel, i, v);
 }
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_commit_vel(const float4* __restrict__ src, Rec rec, float* __restrict__ vel, int begin, int end) {
+k_commit_vel(const float4* __restrict__ src, Rec rec, float* __restrict__ vel, int begin, int end, const int* __restrict__ rangeDev) {
     const int i = begin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
     if (i >= end) return;
+    if (rangeDev && (i < rangeDev[0] || i >= rangeDev[0] + rangeDev[1])) return;
     const float3 v = xyz(src[i]);
     rec_set_vel(rec + i, v);
     if (vel) store3(vel, i, v);
@@ -969,6 +970,8 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
     d.cs = c->cs; d.org = c->org; d.cellLength = c->cellLength;
     d.iBegin = c->actCount < 0 ? 0 : c->actBegin;
     d.iEnd = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
+    d.rangeDev = c->rangeDev;
+    if (c->rangeDev) { d.iBegin = 0; d.iEnd = c->nF; }      // launched over everything, cut on the device
     d.k = kernel_constants(s->radius);
     d.r2list = d.k.r2cut;
     d.dispMax = nullptr; d.dispLimit = 0u; d.posBuild = nullptr;
@@ -977,14 +980,14 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
 
 static int ensure_list(sphk_ctx* c, const DevScene& d) {
     // lists are built for the particles the sweeps will compute (the active range: ghosts of a slab rank need none)
-    if (c->listEpoch == c->searchEpoch && d.iBegin >= c->listBegin && d.iEnd <= c->listEnd) return SPHK_OK;
+    if (c->listEpoch == c->searchEpoch && d.iBegin >= c->listBegin && d.iEnd <= c->listEnd && c->listRangeDev == c->rangeDev) return SPHK_OK;
     if (!c->nbr) {
         const size_t bytes = sizeof(int) * static_cast<size_t>(c->kmax) * (static_cast<size_t>(c->capF) + 2);
         if (cudaMalloc(reinterpret_cast<void**>(&c->nbr), bytes) != cudaSuccess) { cudaGetLastError(); return SPHK_ERR_ALLOC; }
     }
     DevScene b = d;
     b.nbr = c->nbr;
-    c->listBegin = d.iBegin; c->listEnd = d.iEnd;
+    c->listBegin = d.iBegin; c->listEnd = d.iEnd; c->listRangeDev = c->rangeDev;
     c->listHasSkin = c->skin > 0.f;
     if (c->listHasSkin) {
         const float rs = d.k.R * (1.0f + c->skin);
@@ -1089,8 +1092,8 @@ extern "C" int sphk_viscosity(sphk_ctx* c, const sphk_scene* s, float* delta_v, 
     OpViscosity op{tmp, s->fluid.vel, delta_v, rho0, visc, dt};
     const int rc = run_sweep(c, s, op);
     if (rc != SPHK_OK) return rc;
-    const int b = c->actCount < 0 ? 0 : c->actBegin, e = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
-    if (e > b) k_commit_vel<<<sphk_blocks(e - b), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, nullptr, b, e);
+    const int b = (c->actCount < 0 || c->rangeDev) ? 0 : c->actBegin, e = (c->actCount < 0 || c->rangeDev) ? c->nF : c->actBegin + c->actCount;
+    if (e > b) k_commit_vel<<<sphk_blocks(e - b), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, nullptr, b, e, c->rangeDev);
     c->launches++;
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;
@@ -1238,8 +1241,8 @@ extern "C" int sphk_pbd_xsph(sphk_ctx* c, const sphk_scene* s, float xc, float r
     OpXsph op{tmp, xc, rho0};
     const int rc = run_sweep(c, s, op);
     if (rc != SPHK_OK) return rc;
-    const int b = c->actCount < 0 ? 0 : c->actBegin, e = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
-    if (e > b) k_commit_vel<<<sphk_blocks(e - b), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, s->fluid.vel, b, e);
+    const int b = (c->actCount < 0 || c->rangeDev) ? 0 : c->actBegin, e = (c->actCount < 0 || c->rangeDev) ? c->nF : c->actBegin + c->actCount;
+    if (e > b) k_commit_vel<<<sphk_blocks(e - b), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, s->fluid.vel, b, e, c->rangeDev);
     c->launches++;
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;
@@ -1271,6 +1274,14 @@ extern "C" int sphk_set_active_range(sphk_ctx* c, int begin, int count) {
     if (!c) return SPHK_ERR_INVALID;
     if (count >= 0 && (begin < 0 || begin + count > c->nF)) return SPHK_ERR_INVALID;
     c->actBegin = begin; c->actCount = count;
+    c->rangeDev = nullptr;
+    return SPHK_OK;
+}
+
+extern "C" int sphk_set_active_range_device(sphk_ctx* c, const int* device_begin_count) {
+    if (!c) return SPHK_ERR_INVALID;
+    c->rangeDev = device_begin_count;
+    if (device_begin_count) { c->actBegin = 0; c->actCount = -1; }
     return SPHK_OK;
 }
 
@@ -1342,8 +1353,8 @@ extern "C" int sphk_fused_viscosity_surface(sphk_ctx* c, const sphk_scene* s, fl
     OpViscositySurface op{tmp, s->fluid.vel, delta_v, rho0, visc, dt, kappa, airP};
     const int rc = run_sweep(c, s, op);
     if (rc != SPHK_OK) return rc;
-    const int b = c->actCount < 0 ? 0 : c->actBegin, e = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
-    if (e > b) k_commit_vel<<<sphk_blocks(e - b), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, nullptr, b, e);
+    const int b = (c->actCount < 0 || c->rangeDev) ? 0 : c->actBegin, e = (c->actCount < 0 || c->rangeDev) ? c->nF : c->actBegin + c->actCount;
+    if (e > b) k_commit_vel<<<sphk_blocks(e - b), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, nullptr, b, e, c->rangeDev);
     c->launches++;
     SPHK_CUDA_TRY(cudaGetLastError());
     return SPHK_OK;

@@ -254,6 +254,10 @@ class SlabSystem(SphkOps):
         # native exchanges (csrc/sphk_mg.cu): NCCL called directly on the context stream + peer-memory mailboxes for
         # the per-sweep halos.  The torch.distributed path below stays for gloo (CPU tests, ranks sharing one GPU).
         self.mg = None
+        # host-free step assembly (no host synchronisation inside a step; SPHK_SLAB_ASYNC=0 selects the synchronous path)
+        self.async_assembly = os.environ.get("SPHK_SLAB_ASYNC", "1") == "1"
+        self._async_pending = False
+        self._step_async = False
         self.time_assembly = False
         self._assembly_events = []
         if world > 1 and not self.ex.stage and dist.get_backend(group) == "nccl" and os.environ.get("SPHK_SLAB_NATIVE", "1") == "1":
@@ -322,6 +326,10 @@ class SlabSystem(SphkOps):
         check(L.sphk_mg_set_transport(self.mg, C.c_int(transport)), "sphk_mg_set_transport")
         self.transport = transport
         self._cand_from = None
+        self._dev24 = torch.zeros(24, dtype=torch.int32, device=self.device)
+        self._pin24 = torch.zeros(24, dtype=torch.int32).pin_memory()
+        self._pin_misc = torch.zeros(8, dtype=torch.int32).pin_memory()      # [0] from left, [2] from right, [4] mailbox error word
+        self._async_event = torch.cuda.Event()
 
     def _global_boundary(self, scene):
         """Sorted global boundary positions + their masses (SPHSystem.cu:69-71) computed on this GPU."""
@@ -396,6 +404,8 @@ class SlabSystem(SphkOps):
         t0 = time.perf_counter()
         L = self.L
         ev = None
+        self._refresh_ranges()
+        self._step_async = False
         if self.time_assembly:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
@@ -481,10 +491,95 @@ class SlabSystem(SphkOps):
         return ms / n
 
     def _halo(self, what: int, t: torch.Tensor):
+        if self._step_async:             # this step's ranges live on the device
+            check(self.L.sphk_mg_halo_device(self.mg, self.ctx, self._s(), C.c_int(what), _ptr(t), C.c_int(1 if t.dim() == 1 else t.shape[1]),
+                                             C.c_void_p(self._dev24.data_ptr() + 4 * 8), C.c_int(self.cap)), "sphk_mg_halo_device")
+            return
         check(self.L.sphk_mg_halo(self.mg, self.ctx, self._s(), C.c_int(what), _ptr(t), C.c_int(1 if t.dim() == 1 else t.shape[1]),
                                   self._halo_ranges), "sphk_mg_halo")
 
+    # ---- host-free step assembly -----------------------------------------------------------------------------------------
+    def _refresh_ranges(self):
+        """Plane ranges / neighbour counts of the CURRENT sorted set, produced on the device during the last begin_step
+        and copied to pinned host memory: waits for that copy (long finished unless called right after begin_step)."""
+        if not getattr(self, "_async_pending", False):
+            return
+        self._async_event.synchronize()
+        self._async_pending = False
+        pin = self._pin24.tolist()
+        err = int(self._pin_misc[4])
+        if err:
+            raise RuntimeError(f"slab rank {self.rank}: halo mailbox error bits {err:#x} (see sphk_mg_check)")
+        self._ranges = r = plane_ranges(tuple(pin[0:8]), self.w)
+        self.n_gl = r["ghost_l"][1] - r["ghost_l"][0]
+        self.n_own = r["own"][1] - r["own"][0]
+        self.n_gr = r["ghost_r"][1] - r["ghost_r"][0]
+        self.first_plane, self.last_plane = r["first"], r["last"]
+        self.ghost_l, self.ghost_r = r["ghost_l"], r["ghost_r"]
+        self._cand_from = (int(self._pin_misc[0]), int(self._pin_misc[2]))
+
+    def _begin_step_async(self):
+        """begin_step without a host synchronisation.  The host only needs LAST step's plane ranges (to slice the
+        candidates and size this step's search) -- they were computed on the device right after last step's search and
+        arrived in pinned memory while the solver kernels of that step were running.  Everything THIS step derives from
+        its own search (owned range, halo ranges, next candidates, the neighbours' counts) stays on the device:
+        sphk_mg_plane_ranges -> sphk_set_active_range_device / sphk_mg_halo_device / sphk_mg_exchange_ints_async."""
+        t0 = time.perf_counter()
+        L = self.L
+        ev = None
+        if self.time_assembly:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        self._refresh_ranges()
+        arrays = self._carried()
+        r = self._ranges
+        nl, nr = self._cand_from
+        if self.ex.left is None:
+            nl = 0
+        if self.ex.right is None:
+            nr = 0
+        own0, own1 = r["own"]
+        n_own = own1 - own0
+        n_all = nl + n_own + nr
+        if n_all > self.cap:
+            raise RuntimeError(f"slab rank {self.rank}: capacity {self.cap} exceeded by {n_all} local particles")
+        k = len(arrays)
+        widths = (C.c_int * k)(*[1 if a.dim() == 1 else a.shape[1] for a in arrays])
+        src = (C.c_void_p * k)(*[a.data_ptr() for a in arrays])
+        dst = (C.c_void_p * k)(*[a.data_ptr() for a in self._alt])
+        i2 = C.c_int * 2
+        check(L.sphk_mg_exchange_slices(self.mg, C.c_int(k), src, dst, widths,
+                                        i2(r["to_left"][0], r["to_left"][1] - r["to_left"][0]),
+                                        i2(r["to_right"][0], r["to_right"][1] - r["to_right"][0]),
+                                        i2(0, nl), i2(nl + n_own, nr)), "sphk_mg_exchange_slices")
+        for a, d in zip(arrays, self._alt):
+            wd = 1 if a.dim() == 1 else a.shape[1]
+            check(L.sphk_copy(self.ctx, C.c_void_p(d.data_ptr() + 4 * wd * nl), C.c_void_p(a.data_ptr() + 4 * wd * own0),
+                              C.c_int(n_own * wd)), "sphk_copy")
+        self._swap_carried()
+        self._search_all(n_all)
+        d24 = self._dev24.data_ptr()
+        check(L.sphk_mg_plane_ranges(self.mg, _ptr(self.cs_fluid), C.c_int(self.plane_cells), C.c_int(self.w), C.c_void_p(d24),
+                                     C.c_void_p(self._pin24.data_ptr())), "sphk_mg_plane_ranges")
+        pm = self._pin_misc.data_ptr()
+        check(L.sphk_mg_exchange_ints_async(self.mg, C.c_void_p(d24 + 4 * 22), C.c_void_p(d24 + 4 * 23), C.c_int(1),
+                                            C.c_void_p(pm), C.c_void_p(pm + 8)), "sphk_mg_exchange_ints_async")
+        check(L.sphk_mg_check_async(self.mg, C.c_void_p(pm + 16)), "sphk_mg_check_async")
+        self._async_event.record()
+        self._async_pending = True
+        self._step_async = True
+        check(L.sphk_set_active_range_device(self.ctx, C.c_void_p(d24 + 4 * 16)), "sphk_set_active_range_device")
+        if self.use_list:
+            self.set_use_list(True, 150 if self.solver == "pbd" else 0)
+            self.build_neighbor_list()
+        if ev is not None:
+            ev[1].record()
+            self._assembly_events.append(ev)
+        self.comm_s += time.perf_counter() - t0
+
     def begin_step(self):
+        if self.mg is not None and self.async_assembly and self._ranges is not None and getattr(self, "transport", 0) == 1:
+            return self._begin_step_async()
         if self.mg is not None:
             return self._begin_step_native()
         t0 = time.perf_counter()
@@ -596,6 +691,7 @@ class SlabSystem(SphkOps):
         self._push(4, None)
 
     def owned(self, t):
+        self._refresh_ranges()
         return t[self._ranges["own"][0]:self._ranges["own"][1]]
 
     def n_total(self) -> int:
@@ -622,6 +718,7 @@ class SlabSystem(SphkOps):
             self.step_wcsph()
 
     def n_global(self):
+        self._refresh_ranges()
         return int(self.reduce_sum(float(self.n_own)))
 
     def comm_stats(self):
@@ -642,6 +739,7 @@ class SlabSystem(SphkOps):
     def owned_state(self) -> dict:
         """Owned particles of this rank (host arrays)."""
         self.synchronize()
+        self._refresh_ranges()
         a, b = self._ranges["own"]
         g = lambda t: t[a:b].detach().cpu().numpy()  # noqa: E731
         return {"pos": g(self.fluid.pos), "vel": g(self.fluid.vel), "density": g(self.fluid.density)}
@@ -657,6 +755,62 @@ def gather_state(sys_: SlabSystem) -> dict | None:
     out = {k: np.concatenate([o[k] for o in objs], 0) for k in ("pos", "vel", "density")}
     order = np.lexsort((out["pos"][:, 2], out["pos"][:, 1], out["pos"][:, 0]))
     return {k: v[order] for k, v in out.items()}
+
+
+def lattice_keys(pos: np.ndarray, origin, spacing: float) -> np.ndarray:
+    """Identity of a dam-break particle a few steps after the start: the index of the lattice site it started from
+    (displacements are << spacing / 2 during the first steps), as one int64 per particle."""
+    q = np.rint((pos.astype(np.float64) - np.asarray(origin, np.float64)) / float(spacing)).astype(np.int64)
+    q -= q.min(0)
+    ext = q.max(0) + 1
+    return (q[:, 0] * ext[1] + q[:, 1]) * ext[2] + q[:, 2]
+
+
+def parity_check(sys_: "SlabSystem", scene, steps: int = 2) -> dict | None:
+    """Multi-rank result against a single-GPU run of the SAME scene (rank 0's GPU), `steps` steps after the
+    constructor's step 0: every rank's owned particles are gathered on rank 0, matched to the single-GPU particles by
+    their lattice site, and compared -- <= 1e-5 scale-relative on positions and densities (north_star), velocities
+    reported.  Returns the verdict on rank 0 (None elsewhere); raises on a mismatch so that a wrong multi-GPU run can
+    never produce a bench line."""
+    from . import engine, scene as scene_mod
+    for _ in range(steps):
+        sys_.step()
+    st = sys_.owned_state()
+    gathered = [None] * sys_.world if sys_.rank == 0 else None
+    dist.gather_object(st, gathered, dst=0, group=sys_.ex.group)
+    verdict = [None]
+    if sys_.rank == 0:
+        multi = {k: np.concatenate([g[k] for g in gathered], 0) for k in ("pos", "vel", "density")}
+        ref = engine.SphkSystem(scene, device=sys_.device)
+        for _ in range(steps):
+            ref.step()
+        one = ref.state()
+        ref.close()
+        del ref
+        torch.cuda.empty_cache()
+        n = scene.fluid.shape[0]
+        ok_count = multi["pos"].shape[0] == n
+        origin = scene.fluid.min(0)
+        spacing = float(scene_mod.SPACING)
+        km = lattice_keys(multi["pos"], origin, spacing) if ok_count else None
+        ko = lattice_keys(one["pos"], origin, spacing)
+        unique = ok_count and np.unique(km).shape[0] == n and np.unique(ko).shape[0] == n
+        errs = {}
+        if unique:
+            om, oo = np.argsort(km), np.argsort(ko)
+            unique = bool(np.array_equal(km[om], ko[oo]))
+            if unique:
+                for f in ("pos", "density", "vel"):
+                    a, b = multi[f][om].astype(np.float64), one[f][oo].astype(np.float64)
+                    errs[f] = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+        good = bool(unique and errs["pos"] <= 1e-5 and errs["density"] <= 1e-5)
+        verdict[0] = {"parity_checked": True, "parity_ok": good, "steps_after_constructor": steps, "particles_compared": int(n),
+                      "against": "single-GPU run of the same scene on rank 0 (engine.SphkSystem), particles matched by lattice site",
+                      "max_rel_err": errs, "all_particles_present_once": bool(unique)}
+    dist.broadcast_object_list(verdict, src=0, group=sys_.ex.group)
+    if not verdict[0]["parity_ok"]:
+        raise RuntimeError(f"multi-GPU parity check failed: {verdict[0]}")
+    return verdict[0] if sys_.rank == 0 else None
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -700,6 +854,8 @@ def bench_main(args, pkg) -> dict | None:
 
 def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
     s = SlabSystem(sc, rank, world, torch.device("cuda", local))
+    # the result must be RIGHT before it is timed: two steps against a single-GPU run of the same scene (<= 1e-5)
+    parity = parity_check(s, sc, steps=2) if os.environ.get("SPHK_BENCH_PARITY", "1") == "1" else None
     for _ in range(args.warmup):
         s.step()
     sampler = B.ClockSampler(local)
@@ -721,6 +877,7 @@ def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)              # max over ranks
     launches = torch.tensor([s.launch_count() - launches0], dtype=torch.float64, device=s.device)
     dist.all_reduce(launches)
+    s._refresh_ranges()
     own = torch.tensor([float(s.n_own), float(s.n_own)], dtype=torch.float64, device=s.device)
     mx = own.clone()
     dist.all_reduce(own)
@@ -745,6 +902,7 @@ def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
             raise RuntimeError("skipped: a rank could not allocate its pinned buffers")
 
         def down():
+            s._refresh_ranges()
             a, b = s._ranges["own"]
             hpos[:b - a].copy_(s.fluid.pos[a:b], non_blocking=True)
             hvel[:b - a].copy_(s.fluid.vel[a:b], non_blocking=True)
@@ -752,6 +910,7 @@ def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
             return 28 * (b - a)
 
         def up():
+            s._refresh_ranges()
             a, b = s._ranges["own"]
             s.fluid.pos[a:b].copy_(hpos[:b - a], non_blocking=True)
             s.fluid.vel[a:b].copy_(hvel[:b - a], non_blocking=True)
@@ -803,6 +962,7 @@ def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
                      "api": "SlabSystem.step() per rank; every step uploads the rank's owned pos+vel from pinned host buffers "
                             "and downloads pos+vel+density into them (bytes summed over ranks)",
                      "timer": "CUDA events on the compute stream (copies are enqueued on it), max over ranks"}),
+            "parity_checked": bool(parity and parity["parity_checked"]), "max_rel_err": (parity or {}).get("max_rel_err"), "parity": parity,
             "gpu_launches": int(launches.item()), "halo": {"assembly_ms_per_step_device": assembly_ms,
                                                            "assembly_note": "candidate exchange + search of [ghosts|owned] + plane offsets (host read) + count "
                                                                             "exchange + list build, CUDA events on rank 0; the rest of the step is sweeps + one halo kernel each",

@@ -234,6 +234,8 @@ int sphk_export_dots(sphk_ctx* ctx, const sphk_particles* p, float* dot_xyz, flo
  * arrays (contiguous slices) and are mirrored into the packed records. */
 /* restrict every subsequent sweep to particles [begin, begin+count) of the fluid set (count<0: all) */
 int sphk_set_active_range(sphk_ctx* ctx, int begin, int count);
+/* the same with {begin, count} in DEVICE memory, read by the kernels themselves (NULL: back to the host-side range) */
+int sphk_set_active_range_device(sphk_ctx* ctx, const int* device_begin_count);
 /* copy API data of particles [begin, begin+count) into the packed records: what is a bit mask -- 1: vel
  * (scene->fluid.vel), 2: neighbour scalar from `array` (float[n]), 4: pos (scene->fluid.pos; PBD ghosts moved by
  * their owner: counted against the neighbour-list skin like local moves) */
@@ -274,6 +276,20 @@ int  sphk_mg_exchange_slices(sphk_mg_comm* comm, int narrays, const float* const
  * sphk_push_range(what) would (what = 0: an array no record mirrors; 1: array = scene->fluid.vel; 2: neighbour
  * scalar; 4: array = scene->fluid.pos). */
 int  sphk_mg_halo(sphk_mg_comm* comm, sphk_ctx* ctx, const sphk_scene* s, int what, float* array, int width, const int ranges[8]);
+/* Host-free variants (a slab rank's step without a single host synchronisation):
+ * sphk_mg_plane_ranges: from the cell ranges of the freshly sorted local set (cell_start_fluid, plane_cells = cy*cz cells per
+ * x-plane, w owned planes + 2 ghost planes) computes on the device, into device_out24: [0..7] the plane offsets, [8..15] the
+ * halo ranges in sphk_mg_halo's layout, [16..17] the owned range {begin, count} (-> sphk_set_active_range_device),
+ * [18..21] next step's candidate slices, [22..23] their counts (what the neighbours must learn); also copied to pinned host
+ * memory for NEXT step's host-side sizing.  sphk_mg_halo_device: sphk_mg_halo with the ranges read from device memory
+ * (mailbox transport).  sphk_mg_exchange_ints_async / sphk_mg_check_async: as the synchronising calls, device-resident input,
+ * results into pinned host memory when the stream gets there. */
+int  sphk_mg_plane_ranges(sphk_mg_comm* comm, const int* cell_start_fluid, int plane_cells, int w, int* device_out24, int* pinned_host_out24);
+int  sphk_mg_halo_device(sphk_mg_comm* comm, sphk_ctx* ctx, const sphk_scene* s, int what, float* array, int width,
+                         const int* device_ranges8, int max_particles);
+int  sphk_mg_exchange_ints_async(sphk_mg_comm* comm, const int* device_to_left, const int* device_to_right, int count,
+                                 int* pinned_from_left, int* pinned_from_right);
+int  sphk_mg_check_async(sphk_mg_comm* comm, int* pinned_error_bits);
 /* mailbox error word (0 = fine; bit 0/1 timed out waiting for left/right; bit 2/3 size mismatch from left/right).
  * Synchronises the stream. */
 int  sphk_mg_check(sphk_mg_comm* comm, int* error_bits_host);

@@ -174,7 +174,7 @@ def test_choose_cuts_degenerate():
 # ---- the NATIVE begin_step (SlabSystem._begin_step_native over csrc/sphk_mg.cu) with the C entry points replaced by
 # ---- gloo / numpy stand-ins: same host logic as on the GPUs (assembly straight into the scratch twins, swap, counts
 # ---- agreed one step ahead, ordering-contract check, halo ranges), no GPU, no library calls -------------------------
-def _native_worker(rank, world, port, steps, q):
+def _native_worker(rank, world, port, steps, q, use_async=False):
     import ctypes as C
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -254,11 +254,56 @@ def _native_worker(rank, world, port, steps, q):
         def sphk_set_active_range(self, ctx, b, c):
             return 0
 
+        # ---- the host-free variants (device-resident ranges: here plain memory behind the same addresses) ----
+        def sphk_mg_plane_ranges(self, mg, cs_ptr, plane_cells, w_, dev_ptr, pin_ptr):
+            pc, ww = val(plane_cells), val(w_)
+            cs = np.ctypeslib.as_array((C.c_int * ((ww + 2) * pc + 1)).from_address(val(cs_ptr)))
+            s0, s1, s2, s3 = (int(cs[k * pc]) for k in range(4))
+            swm1, sw, sw1, send = int(cs[max(ww - 1, 0) * pc]), int(cs[ww * pc]), int(cs[(ww + 1) * pc]), int(cs[(ww + 2) * pc])
+            fb, fe = s1, (s2 if ww >= 2 else sw1)
+            lb, le = (sw if ww >= 2 else s1), sw1
+            tlb, tle = s1, (min(s3, sw1) if ww >= 2 else sw1)
+            trb, tre = (max(swm1, s1) if ww >= 2 else s1), sw1
+            out = [s0, s1, s2, s3, swm1, sw, sw1, send, fb, fe - fb, lb, le - lb, s0, s1 - s0, sw1, send - sw1, s1, sw1 - s1,
+                   tlb, tle - tlb, trb, tre - trb, tle - tlb, tre - trb]
+            for ptr in (val(dev_ptr), val(pin_ptr)):
+                np.ctypeslib.as_array((C.c_int * 24).from_address(ptr))[:] = out
+            return 0
+
+        def sphk_mg_exchange_ints_async(self, mg, dl, dr, k, pfl, pfr):
+            k = val(k)
+            sends, recvs, bufs = [], [], {}
+            for side, peer, ptr in ((0, left, dl), (1, right, dr)):
+                if peer is not None:
+                    sends.append((torch.tensor(list((C.c_int * k).from_address(val(ptr))), dtype=torch.int32), peer))
+                    bufs[side] = torch.zeros(k, dtype=torch.int32)
+                    recvs.append((bufs[side], peer))
+            p2p(sends, recvs)
+            for side, ptr in ((0, pfl), (1, pfr)):
+                arr = (C.c_int * k).from_address(val(ptr))
+                for i in range(k):
+                    arr[i] = int(bufs[side][i]) if side in bufs else 0
+            return 0
+
+        def sphk_mg_check_async(self, mg, ptr):
+            (C.c_int * 1).from_address(val(ptr))[0] = 0
+            return 0
+
+        def sphk_set_active_range_device(self, ctx, ptr):
+            return 0
+
+        def sphk_mg_halo_device(self, mg, ctx, scene, what, ptr, width, ranges_ptr, maxp):
+            r = list((C.c_int * 8).from_address(val(ranges_ptr)))
+            return self.sphk_mg_halo(mg, ctx, scene, what, ptr, width, r)
+
     class Fluid:
         pass
 
     class FakeSlab:
         _begin_step_native = slabs.SlabSystem._begin_step_native
+        _begin_step_async = slabs.SlabSystem._begin_step_async
+        _refresh_ranges = slabs.SlabSystem._refresh_ranges
+        begin_step = slabs.SlabSystem.begin_step
         _swap_carried = slabs.SlabSystem._swap_carried
         _exchange_ints = slabs.SlabSystem._exchange_ints
         _carried = slabs.SlabSystem._carried
@@ -290,6 +335,10 @@ def _native_worker(rank, world, port, steps, q):
     s.fluid.pos, s.fluid.vel, s.warm = torch.zeros((cap, 3)), torch.zeros((cap, 3)), torch.zeros(cap)
     s.cs_fluid = torch.zeros((w + 2) * CY * CZ + 1, dtype=torch.int32)
     s._ranges, s.use_list, s.comm_s, s.time_assembly, s._assembly_events, s._scene = None, False, 0.0, False, [], None
+    s.async_assembly, s.transport, s._async_pending, s._step_async = use_async, 1, False, False
+    s._dev24, s._pin24, s._pin_misc = torch.zeros(24, dtype=torch.int32), torch.zeros(24, dtype=torch.int32), torch.zeros(8, dtype=torch.int32)
+    s._async_event = type("Ev", (), {"record": lambda self: None, "synchronize": lambda self: None})()
+    used_async = 0
     mine = (plane >= x0) & (plane < x1)
     s.n_own = int(mine.sum())
     s.fluid.pos[:s.n_own] = torch.from_numpy(pos[mine])
@@ -302,11 +351,17 @@ def _native_worker(rank, world, port, steps, q):
             pos = pos + dx
             pos[:, 0] = np.clip(pos[:, 0], 0.05, CX - 0.05)
             pos[:, 1] = np.clip(pos[:, 1], 0.01, CY - 0.01); pos[:, 2] = np.clip(pos[:, 2], 0.01, CZ - 0.01)
+            s._refresh_ranges()
             a0, a1 = s._ranges["own"]
             ids = s.fluid.vel[a0:a1, 0].numpy().astype(np.int64)
             s.fluid.pos[a0:a1] = torch.from_numpy(pos[ids])
-        s._begin_step_native()
+        s.begin_step()
+        used_async += int(s._step_async)
+        if step % 2 == 0:
+            s._refresh_ranges()             # (also exercise a mid-step refresh: the halos below must keep using the device ranges)
         s.warm[:s.fluid.n] = s.warm[:s.fluid.n][s.perm]                  # what step_dfsph's sphk_permute does
+        if step % 2 == 1:
+            s._refresh_ranges()
         r = s._ranges
         (o0, o1), (g0, g1), (h0, h1) = r["own"], r["ghost_l"], r["ghost_r"]
         ids = s.fluid.vel[:h1, 0].numpy().astype(np.int64)
@@ -329,6 +384,7 @@ def _native_worker(rank, world, port, steps, q):
         g3[o0:o1] = s.fluid.pos[o0:o1] * 2.0
         s._halo(0, g3)
         ok &= bool(np.array_equal(g3[:h1].numpy(), pos[ids] * np.float32(2.0)))
+    ok &= used_async == (steps - 1 if use_async else 0)     # the first step sizes itself synchronously, every later one is host-free
     allok = [None] * world
     dist.all_gather_object(allok, bool(ok))
     if rank == 0:
@@ -336,12 +392,15 @@ def _native_worker(rank, world, port, steps, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("use_async", [False, True])
 @pytest.mark.parametrize("world", [2, 3, 4])
-def test_native_begin_step_host_logic_gloo(world):
+def test_native_begin_step_host_logic_gloo(world, use_async):
+    """use_async: the host-free assembly (_begin_step_async: last step's ranges from pinned memory, this step's ranges
+    device-resident) against the same invariants as the synchronous one."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_native_worker, args=(r, world, port, 6, q)) for r in range(world)]
+    procs = [ctx.Process(target=_native_worker, args=(r, world, port, 6, q, use_async)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
