@@ -393,6 +393,84 @@ extern "C" int sphk_reduce_abs_sum(sphk_ctx* c, const float* x, int n, float* ho
     return SPHK_OK;
 }
 
+// ---- device-side scene generation: initSPHSystem(), main.cpp:73-116, without a host-side particle array ---------
+// The fluid block in the reference's push order (i = y outermost, j = x, k = z innermost; main.cpp:76-85), optionally
+// restricted to the x-columns [jBegin, jBegin + jCount) (a slab rank generates only its own columns; the restriction keeps
+// the relative order, which is all the stable sort sees).  Arithmetic as the host code performs it: float multiply, then
+// float add, no contraction -- the positions are bit-identical to scene.py / main.cpp.
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_scene_fluid_block(float* __restrict__ pos, int nz, int jBegin, int jCount, long long count, float ox, float oy, float oz, float spacing) {
+    const long long p = static_cast<long long>(blockIdx.x) * SPHK_BLOCK + threadIdx.x;
+    if (p >= count) return;
+    const int k = static_cast<int>(p % nz);
+    const long long q = p / nz;
+    const int j = jBegin + static_cast<int>(q % jCount);
+    const int i = static_cast<int>(q / jCount);
+    pos[3 * p] = __fadd_rn(ox, __fmul_rn(spacing, static_cast<float>(j)));
+    pos[3 * p + 1] = __fadd_rn(oy, __fmul_rn(spacing, static_cast<float>(i)));
+    pos[3 * p + 2] = __fadd_rn(oz, __fmul_rn(spacing, static_cast<float>(k)));
+}
+
+extern "C" int sphk_scene_fluid_block(float* pos_out, int nx, int ny, int nz, const float origin[3], float spacing, int j_begin,
+                                      int j_count, void* stream) {
+    if (!pos_out || !origin || nx <= 0 || ny <= 0 || nz <= 0 || j_begin < 0 || j_count < 0 || j_begin + j_count > nx) return SPHK_ERR_INVALID;
+    const long long count = static_cast<long long>(ny) * j_count * nz;
+    if (count == 0) return SPHK_OK;
+    const long long blocks = (count + SPHK_BLOCK - 1) / SPHK_BLOCK;
+    if (blocks > 0x7fffffffLL) return SPHK_ERR_INVALID;
+    k_scene_fluid_block<<<static_cast<unsigned int>(blocks), SPHK_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(
+        pos_out, nz, j_begin, j_count, count, origin[0], origin[1], origin[2], spacing);
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+// The six-face boundary shell, main.cpp:89-116: lattice c = 2 * cellSize per axis, point (i,j,k) -> 0.99 * ((i,j,k) / (c - 1) *
+// spaceSize) + 0.005 * spaceSize, pushed as front/back pairs (i in cx, j in cy), top/bottom pairs (i in cx, j in cz - 2),
+// left/right pairs (i in cy - 2, j in cz - 2).  IEEE divide / multiply / add, no contraction.
+__device__ __forceinline__ float shell_coord(int idx, int c, float space) {
+    const float x = __fmul_rn(__fdiv_rn(static_cast<float>(idx), static_cast<float>(c - 1)), space);
+    return __fadd_rn(__fmul_rn(0.99f, x), __fmul_rn(0.005f, space));
+}
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_scene_boundary_shell(float* __restrict__ pos, int cx, int cy, int cz, float sx, float sy, float sz, long long n0, long long n1, long long n2) {
+    const long long p = static_cast<long long>(blockIdx.x) * SPHK_BLOCK + threadIdx.x;
+    if (p >= n0 + n1 + n2) return;
+    int ix, iy, iz;
+    if (p < n0) {                       // front and back
+        const long long q = p >> 1; const int second = static_cast<int>(p & 1);
+        ix = static_cast<int>(q / cy); iy = static_cast<int>(q % cy); iz = second ? cz - 1 : 0;
+    } else if (p < n0 + n1) {           // top and bottom
+        const long long r = p - n0, q = r >> 1; const int second = static_cast<int>(r & 1);
+        ix = static_cast<int>(q / (cz - 2)); iz = static_cast<int>(q % (cz - 2)) + 1; iy = second ? cy - 1 : 0;
+    } else {                            // left and right
+        const long long r = p - n0 - n1, q = r >> 1; const int second = static_cast<int>(r & 1);
+        iy = static_cast<int>(q / (cz - 2)) + 1; iz = static_cast<int>(q % (cz - 2)) + 1; ix = second ? cx - 1 : 0;
+    }
+    pos[3 * p] = shell_coord(ix, cx, sx);
+    pos[3 * p + 1] = shell_coord(iy, cy, sy);
+    pos[3 * p + 2] = shell_coord(iz, cz, sz);
+}
+
+extern "C" long long sphk_scene_boundary_count(const int cell_size[3]) {
+    if (!cell_size) return -1;
+    const long long cx = 2LL * cell_size[0], cy = 2LL * cell_size[1], cz = 2LL * cell_size[2];
+    if (cx < 2 || cy < 2 || cz < 2) return -1;
+    return 2 * cx * cy + 2 * cx * (cz - 2) + 2 * (cy - 2) * (cz - 2);
+}
+
+extern "C" int sphk_scene_boundary_shell(float* pos_out, const int cell_size[3], const float space[3], void* stream) {
+    if (!pos_out || !cell_size || !space) return SPHK_ERR_INVALID;
+    const long long total = sphk_scene_boundary_count(cell_size);
+    if (total <= 0) return SPHK_ERR_INVALID;
+    const int cx = 2 * cell_size[0], cy = 2 * cell_size[1], cz = 2 * cell_size[2];
+    const long long n0 = 2LL * cx * cy, n1 = 2LL * cx * (cz - 2), n2 = 2LL * (cy - 2) * (cz - 2);
+    const long long blocks = (total + SPHK_BLOCK - 1) / SPHK_BLOCK;
+    k_scene_boundary_shell<<<static_cast<unsigned int>(blocks), SPHK_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(
+        pos_out, cx, cy, cz, space[0], space[1], space[2], n0, n1, n2);
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
 // ---- device-side loop control (adaptive DFSPH, DFSPHSolver.cu:187,205-207,347,360) ----------------------------------
 __global__ void k_loop_begin(LoopState* st, int minIter, int maxIter, float threshold, int reduceFrom) {
     st->iters = 0; st->minIter = minIter; st->maxIter = maxIter; st->reduceFrom = reduceFrom;

@@ -24,13 +24,40 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def device_fluid_block(L, lattice, device, stream, j_begin: int = 0, j_count: int | None = None, capacity: int | None = None) -> torch.Tensor:
+    """The fluid block of a device-side scene (sphk_scene_fluid_block): (capacity, 3) float32 tensor whose first
+    ny * j_count * nz rows are the lattice columns [j_begin, j_begin + j_count) in the reference's push order."""
+    (nx, ny, nz), origin = lattice
+    j_count = nx - j_begin if j_count is None else j_count
+    n = ny * j_count * nz
+    out = torch.zeros((max(capacity or n, n, 1), 3), dtype=torch.float32, device=device)
+    from .scene import SPACING
+    check(L.sphk_scene_fluid_block(_ptr(out), C.c_int(nx), C.c_int(ny), C.c_int(nz), (C.c_float * 3)(*origin), C.c_float(float(SPACING)),
+                                   C.c_int(j_begin), C.c_int(j_count), C.c_void_p(stream.cuda_stream)), "sphk_scene_fluid_block")
+    return out
+
+
+def device_boundary_shell(L, params, device, stream) -> torch.Tensor:
+    """The six-face boundary shell of a device-side scene (sphk_scene_boundary_shell)."""
+    cs = (C.c_int * 3)(*[int(c) for c in params.cell_size])
+    n = int(L.sphk_scene_boundary_count(cs))
+    out = torch.empty((n, 3), dtype=torch.float32, device=device)
+    check(L.sphk_scene_boundary_shell(_ptr(out), cs, (C.c_float * 3)(*[float(x) for x in params.space]), C.c_void_p(stream.cuda_stream)),
+          "sphk_scene_boundary_shell")
+    return out
+
+
 class ParticleSet:
     """Device arrays of one SPHParticles object (SPHParticles.h:56-59)."""
 
-    def __init__(self, pos_host: np.ndarray, device):
+    def __init__(self, pos_host, device):
+        """pos_host: (n, 3) host array, or a (n, 3) float32 tensor already on `device` (device-side scenes)."""
         n = pos_host.shape[0]
         self.n = n
-        self.pos = torch.from_numpy(np.ascontiguousarray(pos_host, np.float32)).to(device)
+        if isinstance(pos_host, torch.Tensor):
+            self.pos = pos_host
+        else:
+            self.pos = torch.from_numpy(np.ascontiguousarray(pos_host, np.float32)).to(device)
         self.vel = torch.zeros((n, 3), dtype=torch.float32, device=device)
         self.mass = torch.zeros(n, dtype=torch.float32, device=device)
         self.density = torch.zeros(n, dtype=torch.float32, device=device)
@@ -407,8 +434,12 @@ class SphkSystem(SphkOps):
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.current_stream(self.device)
-        self.fluid = ParticleSet(scene.fluid, self.device)
-        self.boundary = ParticleSet(scene.boundary, self.device)
+        if scene.fluid is None:      # device-side scene: no host particle arrays
+            self.fluid = ParticleSet(device_fluid_block(self.L, scene.lattice, self.device, self.stream), self.device)
+            self.boundary = ParticleSet(device_boundary_shell(self.L, self.p, self.device, self.stream), self.device)
+        else:
+            self.fluid = ParticleSet(scene.fluid, self.device)
+            self.boundary = ParticleSet(scene.boundary, self.device)
         nc = self.p.ncells
         self.cs_fluid = torch.zeros(nc + 1, dtype=torch.int32, device=self.device)
         self.cs_boundary = torch.zeros(nc + 1, dtype=torch.int32, device=self.device)

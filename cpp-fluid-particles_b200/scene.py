@@ -114,9 +114,36 @@ def boundary_lattice(cell_size, space) -> np.ndarray:
 @dataclasses.dataclass
 class Scene:
     name: str
-    fluid: np.ndarray      # (n_fluid, 3) float32
-    boundary: np.ndarray   # (n_boundary, 3) float32
+    fluid: np.ndarray | None      # (n_fluid, 3) float32; None for a device-side scene (generated on the GPU from `lattice`)
+    boundary: np.ndarray | None   # (n_boundary, 3) float32; None for a device-side scene
     params: SceneParams
+    lattice: tuple | None = None  # ((nx, ny, nz), origin): the fluid block of a device-side scene (sphk_scene_fluid_block)
+
+    @property
+    def n_fluid(self) -> int:
+        if self.fluid is not None:
+            return int(self.fluid.shape[0])
+        (nx, ny, nz), _ = self.lattice
+        return nx * ny * nz
+
+    @property
+    def n_boundary(self) -> int:
+        if self.boundary is not None:
+            return int(self.boundary.shape[0])
+        return boundary_count(self.params.cell_size)
+
+
+def boundary_count(cell_size) -> int:
+    """Number of points of the six-face shell (main.cpp:89-116)."""
+    cx, cy, cz = (2 * int(c) for c in cell_size)
+    return 2 * cx * cy + 2 * cx * (cz - 2) + 2 * (cy - 2) * (cz - 2)
+
+
+def lattice_column_planes(nx: int, ox: float, cell_length: float, n_planes: int) -> np.ndarray:
+    """Cell plane (x index) of each of the nx lattice columns of the fluid block -- the host-side partition key of
+    the slab driver, from nx numbers instead of a per-particle array."""
+    x = F(ox) + SPACING * np.arange(nx, dtype=F)
+    return np.clip((x / F(cell_length)).astype(np.int64), 0, n_planes - 1)
 
 
 # name -> (box, (nx, ny, nz), origin).  SURVEY.md section 8(d); origins chosen so that no lattice plane
@@ -136,9 +163,14 @@ _CONFIGS = {
 
 
 def make_scene(name: str = "config0", solver: str = "wcsph", dt: float | None = None, max_iter: int = 0,
-               den_thr: float = 1e-3, div_thr: float = 1e-3, jitter: float = 0.0, seed: int = 42) -> Scene:
+               den_thr: float = 1e-3, div_thr: float = 1e-3, jitter: float = 0.0, seed: int = 42, device_init: bool = False) -> Scene:
+    """device_init: no host-side particle arrays -- the consumer generates the lattice and the boundary shell on the GPU
+    (sphk_scene_fluid_block / sphk_scene_boundary_shell, bit-identical positions)."""
     box, (nx, ny, nz), origin = _CONFIGS[name]
     params = default_params(box, solver, dt, max_iter, den_thr, div_thr)
+    if device_init:
+        assert jitter == 0.0, "device-side scenes are the reference's deterministic lattices"
+        return Scene(name=name, fluid=None, boundary=None, params=params, lattice=((nx, ny, nz), tuple(float(o) for o in origin)))
     fluid = fluid_lattice(nx, ny, nz, origin)
     if jitter > 0.0:
         rng = np.random.default_rng(seed)
@@ -147,14 +179,14 @@ def make_scene(name: str = "config0", solver: str = "wcsph", dt: float | None = 
     return Scene(name=name, fluid=np.ascontiguousarray(fluid), boundary=boundary, params=params)
 
 
-def benchmark_scene(name: str, solver: str) -> Scene:
+def benchmark_scene(name: str, solver: str, device_init: bool = False) -> Scene:
     """BASELINE.md fixed-work settings: WCSPH dt=0.001; DFSPH dt=0.004 with exactly 4+4 iterations
     (negative thresholds, Q11); PBD dt=0.004 with exactly 4 iterations (Q12)."""
     if solver == "dfsph":
-        return make_scene(name, "dfsph", dt=0.004, max_iter=4, den_thr=-1.0, div_thr=-1.0)
+        return make_scene(name, "dfsph", dt=0.004, max_iter=4, den_thr=-1.0, div_thr=-1.0, device_init=device_init)
     if solver == "pbd":
-        return make_scene(name, "pbd", dt=0.004, max_iter=4)
-    return make_scene(name, "wcsph", dt=0.001)
+        return make_scene(name, "pbd", dt=0.004, max_iter=4, device_init=device_init)
+    return make_scene(name, "wcsph", dt=0.001, device_init=device_init)
 
 
 def near_face_count(pos: np.ndarray, cell_length: float, ulps: float = 8.0) -> int:

@@ -44,13 +44,24 @@ import torch.distributed as dist
 
 from . import capi
 from .capi import SphkGrid, check
-from .engine import EPSILON, ParticleSet, SphkOps, _ptr
+from . import scene as scene_mod
+from .engine import EPSILON, ParticleSet, SphkOps, _ptr, device_boundary_shell, device_fluid_block
+
+
+def choose_cuts_weighted(plane_of_column: np.ndarray, weight: int, n_planes: int, world: int) -> list[int]:
+    """choose_cuts for a lattice given by its columns: every column carries `weight` particles."""
+    counts = np.bincount(plane_of_column, minlength=n_planes).astype(np.int64) * int(weight)
+    return _cuts_from_counts(counts, n_planes, world)
 
 
 def choose_cuts(plane_of_particle: np.ndarray, n_planes: int, world: int) -> list[int]:
     """Plane indices X_0=0 < X_1 < ... < X_world=n_planes that balance the particle counts (the CDF along x is
     free: cellStart[x*cy*cz]).  Every slab gets at least one plane."""
     counts = np.bincount(plane_of_particle, minlength=n_planes).astype(np.int64)
+    return _cuts_from_counts(counts, n_planes, world)
+
+
+def _cuts_from_counts(counts: np.ndarray, n_planes: int, world: int) -> list[int]:
     cdf = np.cumsum(counts)
     total = int(cdf[-1])
     cuts = [0]
@@ -214,23 +225,41 @@ class SlabSystem(SphkOps):
         self.plane_cells = cy * cz
         # ---- static partition from the particle CDF along x (host approximation of the hash; exactness is
         # not needed here: a particle one plane off is simply migrated by the first step) --------------------
-        plane = np.clip((scene.fluid[:, 0] / np.float32(p.cell_length)).astype(np.int64), 0, cx - 1)
-        self.cuts = choose_cuts(plane, cx, world)
-        x0, x1 = self.cuts[rank], self.cuts[rank + 1]
-        self.x0, self.x1, self.w = x0, x1, x1 - x0
-        mine = scene.fluid[(plane >= x0) & (plane < x1)]
-        n_total = scene.fluid.shape[0]
+        device_scene = scene.fluid is None
+        n_total = scene.n_fluid
         self._n_scene_fluid = n_total
-        cap = int(max(mine.shape[0], n_total / world) * capacity_factor) + 4096
+        if device_scene:
+            # no host-side particle array.  The CDF comes from the nx lattice columns; the rank generates
+            # its own columns on the device, the boundary shell is generated, searched and weighed on the device and the
+            # rank's planes are cut out of the sorted set as one contiguous slice.
+            (nx, ny, nz), origin = scene.lattice
+            col_plane = scene_mod.lattice_column_planes(nx, origin[0], p.cell_length, cx)
+            self.cuts = choose_cuts_weighted(col_plane, ny * nz, cx, world)
+            x0, x1 = self.cuts[rank], self.cuts[rank + 1]
+            self.x0, self.x1, self.w = x0, x1, x1 - x0
+            cols = np.nonzero((col_plane >= x0) & (col_plane < x1))[0]
+            j_begin, j_count = (int(cols[0]), int(cols.shape[0])) if cols.shape[0] else (0, 0)
+            n_mine = ny * j_count * nz
+            cap = int(max(n_mine, n_total / world) * capacity_factor) + 4096
+            fluid_dev = device_fluid_block(self.L, scene.lattice, self.device, self.stream, j_begin, j_count, capacity=cap)
+            bpos, bmass = self._global_boundary_device(scene, x0, x1)
+        else:
+            plane = np.clip((scene.fluid[:, 0] / np.float32(p.cell_length)).astype(np.int64), 0, cx - 1)
+            self.cuts = choose_cuts(plane, cx, world)
+            x0, x1 = self.cuts[rank], self.cuts[rank + 1]
+            self.x0, self.x1, self.w = x0, x1, x1 - x0
+            mine = scene.fluid[(plane >= x0) & (plane < x1)]
+            n_mine = mine.shape[0]
+            cap = int(max(n_mine, n_total / world) * capacity_factor) + 4096
+            # ---- boundary: masses from the GLOBAL boundary set (every rank computes them once), then the subset
+            # in this rank's planes [x0-1, x1+1) ---------------------------------------------------------------
+            bpos, bmass = self._global_boundary(scene)
+            bplane = self._bplane
+            sel = (bplane >= x0 - 1) & (bplane < x1 + 1)
+            bpos, bmass = bpos[sel], bmass[sel]
+            if bpos.shape[0] == 0:                         # keep the C-ABI happy: one far-away massless dummy
+                bpos = np.full((1, 3), -1.0e3, np.float32); bmass = np.zeros(1, np.float32)
         self.cap = cap
-        # ---- boundary: masses from the GLOBAL boundary set (every rank computes them once), then the subset
-        # in this rank's planes [x0-1, x1+1) -------------------------------------------------------------------
-        bpos, bmass = self._global_boundary(scene)
-        bplane = self._bplane
-        sel = (bplane >= x0 - 1) & (bplane < x1 + 1)
-        bpos, bmass = bpos[sel], bmass[sel]
-        if bpos.shape[0] == 0:                         # keep the C-ABI happy: one far-away massless dummy
-            bpos = np.full((1, 3), -1.0e3, np.float32); bmass = np.zeros(1, np.float32)
         # ---- local context ---------------------------------------------------------------------------------
         self.local_cs = (self.w + 2, cy, cz)
         g = SphkGrid()
@@ -238,12 +267,15 @@ class SlabSystem(SphkOps):
         g.cell_length = p.cell_length
         g.origin[:] = [x0 - 1, 0, 0]
         self.ncells_local = (self.w + 2) * cy * cz
-        self.fluid = ParticleSet(np.zeros((cap, 3), np.float32), self.device)   # capacity-sized arrays
-        self.fluid.n = mine.shape[0]                                             # current local count
-        self.fluid.pos[:mine.shape[0]] = torch.from_numpy(np.ascontiguousarray(mine)).to(self.device)
+        if device_scene:
+            self.fluid = ParticleSet(fluid_dev, self.device)                      # capacity-sized, first n_mine rows generated
+        else:
+            self.fluid = ParticleSet(np.zeros((cap, 3), np.float32), self.device)   # capacity-sized arrays
+            self.fluid.pos[:n_mine] = torch.from_numpy(np.ascontiguousarray(mine)).to(self.device)
+        self.fluid.n = n_mine                                                    # current local count
         self.fluid.mass.fill_(p.m0)                     # SPHSystem.cu:73
         self.boundary = ParticleSet(bpos, self.device)
-        self.boundary.mass.copy_(torch.from_numpy(bmass))
+        self.boundary.mass.copy_(bmass if isinstance(bmass, torch.Tensor) else torch.from_numpy(bmass))
         self.cs_fluid = torch.zeros(self.ncells_local + 1, dtype=torch.int32, device=self.device)
         self.cs_boundary = torch.zeros(self.ncells_local + 1, dtype=torch.int32, device=self.device)
         self.ctx = C.c_void_p()
@@ -268,7 +300,7 @@ class SlabSystem(SphkOps):
         self._scene = None
         self._G = (C.c_float * 3)(*[float(x) for x in p.gravity])
         self._space = (C.c_float * 3)(*[float(x) for x in p.space])
-        self.n_own, self.n_gl, self.n_gr = mine.shape[0], 0, 0
+        self.n_own, self.n_gl, self.n_gr = n_mine, 0, 0
         self._ranges = None            # plane ranges of the last sorted local set
         # boundary: already in global sorted order -> identity permutation; masses given (not recomputed)
         # (the search's gather packs mass[s] of the sorted slot s into the records: the masses set above)
@@ -330,6 +362,33 @@ class SlabSystem(SphkOps):
         self._pin24 = torch.zeros(24, dtype=torch.int32).pin_memory()
         self._pin_misc = torch.zeros(8, dtype=torch.int32).pin_memory()      # [0] from left, [2] from right, [4] mailbox error word
         self._async_event = torch.cuda.Event()
+
+    def _global_boundary_device(self, scene, x0: int, x1: int):
+        """Device-side twin of _global_boundary: the shell is generated (sphk_scene_boundary_shell), searched and weighed
+        (SPHSystem.cu:69-71) on this GPU; the sorted set is x-major, so the boundary particles of this rank's planes
+        [x0 - 1, x1 + 1) are ONE contiguous slice of it -- cut out device to device (the host reads two offsets)."""
+        p = self.p
+        g = SphkGrid()
+        g.cell_size[:] = [int(c) for c in p.cell_size]
+        g.cell_length = p.cell_length
+        g.origin[:] = [0, 0, 0]
+        b = ParticleSet(device_boundary_shell(self.L, p, self.device, self.stream), self.device)
+        nb = b.n
+        cs = torch.zeros(p.ncells + 1, dtype=torch.int32, device=self.device)
+        ctx = C.c_void_p()
+        check(self.L.sphk_create(C.byref(ctx), C.c_int(1), C.c_int(nb), C.byref(g), C.c_void_p(self.stream.cuda_stream)))
+        pa = b.abi()
+        check(self.L.sphk_neighbor_search(ctx, 1, C.byref(pa), _ptr(cs)))
+        check(self.L.sphk_boundary_mass(ctx, C.byref(pa), _ptr(cs), C.c_float(p.rho_boundary), C.c_float(p.radius)))
+        pc = int(p.cell_size[1]) * int(p.cell_size[2])
+        lo_plane, hi_plane = max(x0 - 1, 0), min(x1 + 1, int(p.cell_size[0]))
+        a, e = (int(v) for v in cs[torch.tensor([lo_plane * pc, hi_plane * pc], device=self.device)].cpu().tolist())
+        check(self.L.sphk_synchronize(ctx))
+        self.L.sphk_destroy(ctx)
+        if e <= a:                                      # keep the C-ABI happy: one far-away massless dummy
+            return (torch.full((1, 3), -1.0e3, dtype=torch.float32, device=self.device),
+                    torch.zeros(1, dtype=torch.float32, device=self.device))
+        return b.pos[a:e].clone(), b.mass[a:e].clone()
 
     def _global_boundary(self, scene):
         """Sorted global boundary positions + their masses (SPHSystem.cu:69-71) computed on this GPU."""
@@ -788,9 +847,9 @@ def parity_check(sys_: "SlabSystem", scene, steps: int = 2) -> dict | None:
         ref.close()
         del ref
         torch.cuda.empty_cache()
-        n = scene.fluid.shape[0]
+        n = scene.n_fluid
         ok_count = multi["pos"].shape[0] == n
-        origin = scene.fluid.min(0)
+        origin = scene.fluid.min(0) if scene.fluid is not None else np.asarray(scene.lattice[1], np.float32)
         spacing = float(scene_mod.SPACING)
         km = lattice_keys(multi["pos"], origin, spacing) if ok_count else None
         ko = lattice_keys(one["pos"], origin, spacing)
@@ -829,8 +888,8 @@ def bench_main(args, pkg) -> dict | None:
     solver = args.workload
     strong = getattr(args, "scaling", "weak") == "strong"
     scene_name = args.scene or ("2m" if strong else B.SCENE_OF_N[world])
-    sc = pkg.scene.benchmark_scene(scene_name, solver)
-    n = sc.fluid.shape[0]
+    sc = pkg.scene.benchmark_scene(scene_name, solver, device_init=os.environ.get("SPHK_BENCH_DEVICE_SCENE", "1") == "1")
+    n = sc.n_fluid
     # a rank that dies must take the job down at once (its neighbours would wait for it inside a collective), and a job
     # that stops making progress must not sit on the GPUs: bounded by a watchdog
     import threading
@@ -951,7 +1010,8 @@ def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
     return {"metric": "particle-steps/sec (dam-break)", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": B.workload_name(scene_name, solver), "n_fluid": n, "n_boundary": int(sc.boundary.shape[0]),
+            "config": {"workload": B.workload_name(scene_name, solver), "n_fluid": n, "n_boundary": int(sc.n_boundary),
+                       "scene_init": "device-side (sphk_scene_fluid_block / sphk_scene_boundary_shell: no host particle arrays)" if sc.fluid is None else "host arrays",
                        "cells": list(sc.params.cell_size), "parallelism": f"x-slabs x{world}, halo = 1 cell plane, {transport}",
                        "per_gpu_particles_max": int(mx[0].item()), "load_imbalance": float(mx[0].item() * world / own[0].item()),
                        "l2": "inputs larger than L2 (packed records + neighbour list per rank > 126 MB); no flush"},

@@ -223,6 +223,17 @@ int sphk_pbd_xsph(sphk_ctx* ctx, const sphk_scene* s, float c, float rho0);
 /* Builds the per-step neighbour list now (sweeps otherwise build it lazily on first use). */
 int sphk_build_neighbor_list(sphk_ctx* ctx, const sphk_scene* s);
 
+/* ---- scene generation on the device: initSPHSystem(), main.cpp:73-116 ---------------------------------------
+ * The dam-break scene without a host-side particle array: positions are bit-identical to the host code's (same float
+ * operations in the same order, no contraction) and in the reference's push order.
+ * fluid block nx * ny * nz at `origin` with `spacing` (main.cpp:76-85: y outermost, then x, z innermost), restricted to the
+ * x-columns [j_begin, j_begin + j_count) -- a slab rank generates only its own columns; pos_out: float3[ny * j_count * nz]. */
+int sphk_scene_fluid_block(float* pos_out, int nx, int ny, int nz, const float origin[3], float spacing, int j_begin, int j_count,
+                           void* stream);
+/* six-face boundary shell of the box `space` on the lattice 2 * cell_size (main.cpp:89-116); pos_out: float3[count] */
+long long sphk_scene_boundary_count(const int cell_size[3]);
+int sphk_scene_boundary_shell(float* pos_out, const int cell_size[3], const float space[3], void* stream);
+
 /* ---- render export: generate_dots_CUDA, vbo.cu:26-44 -----------------------------------------------
  * dot[i] = pos[i]; colour[i] from density[i] (blue below 0.75, blend to white at 1.0, blend to pink above).  Plain
  * device buffers instead of a mapped GL vertex buffer; synchronises like the reference (vbo.cu:49). */

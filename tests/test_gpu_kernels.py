@@ -306,6 +306,37 @@ def test_list_overflow_falls_back_exactly(pkg, built, O):
     s.close(); s2.close()
 
 
+@pytest.mark.parametrize("name", ["mini", "config0", "200k", "slabtest"])
+def test_device_side_scene_bit_identical(pkg, built, name):
+    """sphk_scene_fluid_block / sphk_scene_boundary_shell against scene.py (= main.cpp:73-116 on the host):
+    same positions bit for bit, same push order; also a column sub-range (what a slab rank generates)."""
+    torch = _torch()
+    from cpp_fluid_particles_b200 import capi, engine
+    L = capi.sphk()
+    host = pkg.scene.make_scene(name)
+    dev = pkg.scene.make_scene(name, device_init=True)
+    assert dev.fluid is None and dev.n_fluid == host.fluid.shape[0] and dev.n_boundary == host.boundary.shape[0]
+    d = torch.device("cuda:0")
+    st = torch.cuda.current_stream(d)
+    f = engine.device_fluid_block(L, dev.lattice, d, st)
+    b = engine.device_boundary_shell(L, dev.params, d, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(f.cpu().numpy()), bits(host.fluid)), "fluid block differs from main.cpp:76-85"
+    assert np.array_equal(bits(b.cpu().numpy()), bits(host.boundary)), "boundary shell differs from main.cpp:89-116"
+    (nx, ny, nz), _ = dev.lattice
+    jb, jc = nx // 3, nx // 2
+    sub = engine.device_fluid_block(L, dev.lattice, d, st, jb, jc).cpu().numpy()
+    want = host.fluid.reshape(ny, nx, nz, 3)[:, jb:jb + jc].reshape(-1, 3)
+    assert np.array_equal(bits(sub), bits(np.ascontiguousarray(want)))
+    # a whole system built from the device-side scene equals the one built from the host arrays
+    a, c = engine.SphkSystem(pkg.scene.benchmark_scene(name, "dfsph")), engine.SphkSystem(pkg.scene.benchmark_scene(name, "dfsph", device_init=True))
+    a.step(); c.step()
+    sa, sc_ = a.state(), c.state()
+    assert np.array_equal(bits(sa["pos"]), bits(sc_["pos"])) and np.array_equal(bits(sa["density"]), bits(sc_["density"]))
+    assert np.array_equal(bits(sa["massB"]), bits(sc_["massB"]))
+    a.close(); c.close()
+
+
 def test_particles_advect_raw(pkg, built):
     """Particles::advect (Particles.cu:28-36) on raw arrays."""
     import ctypes as C

@@ -34,6 +34,19 @@ def test_slabs_match_single_gpu_shared_device(built, solver, world):
     assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
 
 
+@pytest.mark.parametrize("solver", ["dfsph", "pbd"])
+def test_slabs_device_side_scene(built, solver):
+    """every rank generates its own lattice columns and the boundary shell on the device (no host-side
+    particle array, boundary planes cut out of the sorted shell as one slice) -- against the single-GPU run built from
+    the host arrays."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device")
+    out = _run(2, ["--backend", "gloo", "--same-gpu", "--solver", solver, "--steps", "3", "--device-scene"])
+    assert out["ok"], out
+    assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
+
+
 @pytest.mark.parametrize("transport,solver", [("mailbox", "dfsph"), ("mailbox", "wcsph"), ("mailbox", "pbd"),
                                               ("nccl", "dfsph"), ("nccl", "wcsph"), ("torch", "dfsph")])
 def test_slabs_match_single_gpu_nccl(built, solver, transport):

@@ -19,6 +19,7 @@ ap.add_argument("--solver", default="dfsph")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--same-gpu", action="store_true")
 ap.add_argument("--jitter", type=float, default=0.0)
+ap.add_argument("--device-scene", action="store_true", help="ranks generate their columns / the boundary shell on the device (no host arrays)")
 a = ap.parse_args()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local = 0 if a.same_gpu else int(os.environ.get("LOCAL_RANK", rank))
@@ -27,7 +28,11 @@ dist.init_process_group(a.backend)
 b = pkg.scene.benchmark_scene(a.scene, a.solver)
 sc = pkg.scene.make_scene(a.scene, solver=a.solver, dt=b.params.dt, max_iter=b.params.max_iter,
                           den_thr=b.params.density_error_threshold, div_thr=b.params.divergence_error_threshold, jitter=a.jitter)
-s = slabs.SlabSystem(sc, rank, world, torch.device("cuda", local))
+sc_ranks = sc
+if a.device_scene:      # the ranks build the scene on the device; the single-GPU reference below keeps the host arrays
+    sc_ranks = pkg.scene.make_scene(a.scene, solver=a.solver, dt=b.params.dt, max_iter=b.params.max_iter,
+                                    den_thr=b.params.density_error_threshold, div_thr=b.params.divergence_error_threshold, device_init=True)
+s = slabs.SlabSystem(sc_ranks, rank, world, torch.device("cuda", local))
 states = [slabs.gather_state(s)]
 for _ in range(a.steps):
     s.step()
