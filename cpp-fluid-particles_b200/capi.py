@@ -18,7 +18,7 @@ LIBSPHK = os.path.join(HERE, "libsphk.so")
 LIBHOST = os.path.join(HERE, "libsphhost.so")
 
 SPHK_FUNCTIONS = [
-    "sphk_create", "sphk_destroy", "sphk_set_option", "sphk_synchronize", "sphk_error_string", "sphk_launch_count",
+    "sphk_create", "sphk_destroy", "sphk_set_option", "sphk_set_grid", "sphk_synchronize", "sphk_error_string", "sphk_launch_count",
     "sphk_device_rcp", "sphk_neighbor_search", "sphk_permute", "sphk_refresh", "sphk_boundary_mass", "sphk_fill",
     "sphk_gravity", "sphk_viscosity", "sphk_color_grad", "sphk_surface", "sphk_density", "sphk_pressure",
     "sphk_pressure_force", "sphk_advect", "sphk_dfsph_density_alpha", "sphk_dfsph_div_error", "sphk_dfsph_div_correct",

@@ -256,6 +256,22 @@ extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
     }
 }
 
+// Re-targets the context at another (sub-)grid of the same cell length: a slab rank whose cuts moved (load re-balancing)
+// keeps its context, buffers and lists' storage; both particle sets must be searched again before the next sweep.
+extern "C" int sphk_set_grid(sphk_ctx* c, const sphk_grid* grid) {
+    if (!c || !grid || grid->cell_size[0] <= 0 || grid->cell_size[1] <= 0 || grid->cell_size[2] <= 0) return SPHK_ERR_INVALID;
+    if (grid->cell_length != c->cellLength) return SPHK_ERR_INVALID;
+    c->cs = make_int3(grid->cell_size[0], grid->cell_size[1], grid->cell_size[2]);
+    c->org = make_int3(grid->origin[0], grid->origin[1], grid->origin[2]);
+    c->ncells = c->cs.x * c->cs.y * c->cs.z;
+    c->endBit = 1;
+    while (c->endBit < 32 && (1ll << c->endBit) <= static_cast<long long>(c->ncells)) ++c->endBit;
+    c->fluidSearched = false; c->boundarySearched = false; c->permValid = false;
+    c->listEpoch = ~0ull; c->sTag = nullptr;
+    c->actBegin = 0; c->actCount = -1; c->rangeDev = nullptr;
+    return SPHK_OK;
+}
+
 extern "C" int sphk_synchronize(sphk_ctx* c) {
     if (!c) return SPHK_ERR_INVALID;
     SPHK_CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -61,6 +61,14 @@ def choose_cuts(plane_of_particle: np.ndarray, n_planes: int, world: int) -> lis
     return _cuts_from_counts(counts, n_planes, world)
 
 
+def skew_cuts(cuts: list[int], skew: int, n_planes: int) -> list[int]:
+    world = len(cuts) - 1
+    out = list(cuts)
+    for g in range(1, world):
+        out[g] = min(max(cuts[g] + skew, out[g - 1] + 1), n_planes - (world - g))
+    return out
+
+
 def _cuts_from_counts(counts: np.ndarray, n_planes: int, world: int) -> list[int]:
     cdf = np.cumsum(counts)
     total = int(cdf[-1])
@@ -211,7 +219,8 @@ class SlabSystem(SphkOps):
 
     HISTORY = {"dfsph": 1, "wcsph": 0, "pbd": 3}      # extra floats per particle that migrate with it
 
-    def __init__(self, scene, rank: int, world: int, device, capacity_factor: float = 1.6, group=None):
+    def __init__(self, scene, rank: int, world: int, device, capacity_factor: float = 1.6, group=None, cut_skew: int = 0):
+        """cut_skew: shifts the interior cuts by that many planes off the balanced position (tests of the re-balancing)."""
         self.L = capi.sphk()
         self.p = scene.params
         self.rank, self.world = rank, world
@@ -234,7 +243,7 @@ class SlabSystem(SphkOps):
             # rank's planes are cut out of the sorted set as one contiguous slice.
             (nx, ny, nz), origin = scene.lattice
             col_plane = scene_mod.lattice_column_planes(nx, origin[0], p.cell_length, cx)
-            self.cuts = choose_cuts_weighted(col_plane, ny * nz, cx, world)
+            self.cuts = skew_cuts(choose_cuts_weighted(col_plane, ny * nz, cx, world), cut_skew, cx)
             x0, x1 = self.cuts[rank], self.cuts[rank + 1]
             self.x0, self.x1, self.w = x0, x1, x1 - x0
             cols = np.nonzero((col_plane >= x0) & (col_plane < x1))[0]
@@ -245,7 +254,7 @@ class SlabSystem(SphkOps):
             bpos, bmass = self._global_boundary_device(scene, x0, x1)
         else:
             plane = np.clip((scene.fluid[:, 0] / np.float32(p.cell_length)).astype(np.int64), 0, cx - 1)
-            self.cuts = choose_cuts(plane, cx, world)
+            self.cuts = skew_cuts(choose_cuts(plane, cx, world), cut_skew, cx)
             x0, x1 = self.cuts[rank], self.cuts[rank + 1]
             self.x0, self.x1, self.w = x0, x1, x1 - x0
             mine = scene.fluid[(plane >= x0) & (plane < x1)]
@@ -279,7 +288,8 @@ class SlabSystem(SphkOps):
         self.cs_fluid = torch.zeros(self.ncells_local + 1, dtype=torch.int32, device=self.device)
         self.cs_boundary = torch.zeros(self.ncells_local + 1, dtype=torch.int32, device=self.device)
         self.ctx = C.c_void_p()
-        check(self.L.sphk_create(C.byref(self.ctx), C.c_int(cap), C.c_int(self.boundary.n), C.byref(g),
+        # (boundary capacity: the whole shell -- the rank's slice grows and shrinks when the cuts move)
+        check(self.L.sphk_create(C.byref(self.ctx), C.c_int(cap), C.c_int(max(self.boundary.n, int(self._bglobal[0].shape[0]))), C.byref(g),
                                  C.c_void_p(self.stream.cuda_stream)), "sphk_create")
         self._alloc_solver_buffers(cap)
         self.use_list = True
@@ -288,6 +298,8 @@ class SlabSystem(SphkOps):
         self.mg = None
         # host-free step assembly (no host synchronisation inside a step; SPHK_SLAB_ASYNC=0 selects the synchronous path)
         self.async_assembly = os.environ.get("SPHK_SLAB_ASYNC", "1") == "1"
+        self.rebalance_every = int(os.environ.get("SPHK_SLAB_REBALANCE", "50"))   # steps between cut adjustments (0: never)
+        self._step_no, self.rebalanced, self.imbalance = -1, 0, 1.0
         self._async_pending = False
         self._step_async = False
         self.time_assembly = False
@@ -385,10 +397,19 @@ class SlabSystem(SphkOps):
         a, e = (int(v) for v in cs[torch.tensor([lo_plane * pc, hi_plane * pc], device=self.device)].cpu().tolist())
         check(self.L.sphk_synchronize(ctx))
         self.L.sphk_destroy(ctx)
+        planes = torch.arange(0, int(p.cell_size[0]) + 1, device=self.device) * pc
+        self._bglobal = (b.pos, b.mass, cs[planes].cpu().numpy())       # sorted shell + plane offsets: re-sliced when the cuts move
+        return self._boundary_slice(x0, x1)
+
+    def _boundary_slice(self, x0: int, x1: int):
+        """Boundary particles of the global planes [x0 - 1, x1 + 1) out of the sorted global shell (device tensors)."""
+        bpos, bmass, plane_start = self._bglobal
+        cx = plane_start.shape[0] - 1
+        a, e = int(plane_start[max(x0 - 1, 0)]), int(plane_start[min(x1 + 1, cx)])
         if e <= a:                                      # keep the C-ABI happy: one far-away massless dummy
             return (torch.full((1, 3), -1.0e3, dtype=torch.float32, device=self.device),
                     torch.zeros(1, dtype=torch.float32, device=self.device))
-        return b.pos[a:e].clone(), b.mass[a:e].clone()
+        return bpos[a:e].clone(), bmass[a:e].clone()
 
     def _global_boundary(self, scene):
         """Sorted global boundary positions + their masses (SPHSystem.cu:69-71) computed on this GPU."""
@@ -411,6 +432,7 @@ class SlabSystem(SphkOps):
         # plane of each SORTED boundary particle from the cell ranges
         plane_start = csh[np.arange(0, p.cell_size[0] + 1) * (int(p.cell_size[1]) * int(p.cell_size[2]))]
         self._bplane = np.searchsorted(plane_start, np.arange(nb), side="right") - 1
+        self._bglobal = (torch.from_numpy(pos).to(self.device), torch.from_numpy(mass).to(self.device), plane_start)
         self.L.sphk_destroy(ctx)
         return pos, mass
 
@@ -767,7 +789,72 @@ class SlabSystem(SphkOps):
         dist.all_reduce(t, group=self.ex.group)
         return float(t.item())
 
+    # ---- load re-balancing ("re-balance every K steps") ------------------------------------------------------------
+    def rebalance(self) -> bool:
+        """Moves every interior cut by at most ONE plane towards the position that balances the current particle counts
+        (a dam-break sloshes: the block that starts in one corner spreads over the whole box).  No particle data moves
+        here: a cut that shifts by one plane only changes which of the planes a rank already exchanges as candidates
+        count as owned -- the next step's sort does the rest -- provided the candidates cover THREE planes per side for
+        that one step (the moved cut uses up the one-plane margin the usual two planes leave for particle motion).
+        Collective; synchronises (it reads w + 1 cell offsets and agrees on counts), so it runs every K steps only."""
+        if self.world == 1 or self._ranges is None:
+            return False
+        self._refresh_ranges()
+        pc, w = self.plane_cells, self.w
+        offs = self.cs_fluid[torch.arange(1, w + 2, device=self.device) * pc].cpu().numpy().astype(np.int64)   # planes 1 .. w+1
+        mine = (self.x0, np.diff(offs).tolist())
+        everybody = [None] * self.world
+        dist.all_gather_object(everybody, mine, group=self.ex.group)
+        cx = int(self.p.cell_size[0])
+        counts = np.zeros(cx, np.int64)
+        for x0_, c in everybody:
+            counts[x0_:x0_ + len(c)] = c
+        ideal = _cuts_from_counts(counts, cx, self.world)
+        new = list(self.cuts)
+        for g in range(1, self.world):
+            new[g] = self.cuts[g] + int(np.sign(ideal[g] - self.cuts[g]))
+            new[g] = min(max(new[g], new[g - 1] + 1), cx - (self.world - g))
+        self.imbalance = float(max(sum(c) for _, c in everybody) * self.world / max(int(counts.sum()), 1))
+        if new == list(self.cuts):
+            return False
+        # candidates of the next exchange: three planes per side (offsets of the CURRENT sorted set)
+        s1, sw1 = int(offs[0]), int(offs[w])
+        s4 = int(offs[min(3, w)])
+        swm2 = int(offs[max(w - 3, 0)])
+        r = self._ranges
+        r["to_left"], r["to_right"] = (s1, min(s4, sw1)), (max(swm2, s1), sw1)
+        if self.mg is not None:
+            fl, fr = self._exchange_ints([r["to_left"][1] - r["to_left"][0]], [r["to_right"][1] - r["to_right"][0]])
+            self._cand_from = (fl[0], fr[0])
+        # the new local grid
+        self.cuts = new
+        self.x0, self.x1 = new[self.rank], new[self.rank + 1]
+        self.w = self.x1 - self.x0
+        cy, cz = int(self.p.cell_size[1]), int(self.p.cell_size[2])
+        self.local_cs = (self.w + 2, cy, cz)
+        g = SphkGrid()
+        g.cell_size[:] = list(self.local_cs)
+        g.cell_length = self.p.cell_length
+        g.origin[:] = [self.x0 - 1, 0, 0]
+        check(self.L.sphk_set_grid(self.ctx, C.byref(g)), "sphk_set_grid")
+        self.ncells_local = (self.w + 2) * cy * cz
+        self.cs_fluid = torch.zeros(self.ncells_local + 1, dtype=torch.int32, device=self.device)
+        self.cs_boundary = torch.zeros(self.ncells_local + 1, dtype=torch.int32, device=self.device)
+        bpos, bmass = self._boundary_slice(self.x0, self.x1)
+        self.boundary = ParticleSet(bpos, self.device)
+        self.boundary.mass.copy_(bmass)
+        self._scene = None
+        if hasattr(self, "_bounds_idx"):
+            del self._bounds_idx
+        self.search_boundary()                          # (masses are given: the search only sorts and packs them)
+        self._step_async = False
+        self.rebalanced += 1
+        return True
+
     def step(self):
+        self._step_no += 1
+        if self.rebalance_every > 0 and self._step_no % self.rebalance_every == 0:
+            self.rebalance()
         self.begin_step()
         if self.solver == "dfsph":
             self.step_dfsph()

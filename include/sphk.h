@@ -101,6 +101,9 @@ enum {
 int  sphk_create(sphk_ctx** ctx, int max_fluid, int max_boundary, const sphk_grid* grid, void* stream);
 void sphk_destroy(sphk_ctx* ctx);
 int  sphk_set_option(sphk_ctx* ctx, int option, int value);
+/* re-target the context at another (sub-)grid with the same cell length (a slab rank whose cuts moved): both particle
+ * sets must be searched again before the next sweep; capacities and buffers are kept */
+int  sphk_set_grid(sphk_ctx* ctx, const sphk_grid* grid);
 int  sphk_synchronize(sphk_ctx* ctx);
 const char* sphk_error_string(int code);
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */

@@ -34,6 +34,22 @@ def test_slabs_match_single_gpu_shared_device(built, solver, world):
     assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
 
 
+@pytest.mark.parametrize("solver,world", [("dfsph", 2), ("pbd", 3), ("wcsph", 3)])
+def test_slabs_rebalance_cuts(built, solver, world):
+    """SURVEY 8e "re-balance every K steps": the run starts with its interior cuts 3 planes off balance and re-balances
+    every 2 steps (each event moves a cut by one plane; the ranks' grids, boundary slices and candidate planes follow).
+    The result must stay the single-GPU result, the cuts must come back and the load imbalance must fall below 1.1."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device")
+    out = _run(world, ["--backend", "gloo", "--same-gpu", "--solver", solver, "--steps", "12", "--jitter", "0.001", "--skew", "3",
+                       "--rebalance", "2"])
+    assert out["ok"], out
+    assert out["rebalanced"] >= 3 and out["cuts_final"] != out["cuts_initial"], out
+    assert out["imbalance_at_last_rebalance"] < 1.1, out
+    assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
+
+
 @pytest.mark.parametrize("solver", ["dfsph", "pbd"])
 def test_slabs_device_side_scene(built, solver):
     """every rank generates its own lattice columns and the boundary shell on the device (no host-side

@@ -19,6 +19,8 @@ ap.add_argument("--solver", default="dfsph")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--same-gpu", action="store_true")
 ap.add_argument("--jitter", type=float, default=0.0)
+ap.add_argument("--rebalance", type=int, default=-1, help="re-balance the cuts every K steps (default: the driver's own setting)")
+ap.add_argument("--skew", type=int, default=0, help="start with the interior cuts this many planes off balance")
 ap.add_argument("--device-scene", action="store_true", help="ranks generate their columns / the boundary shell on the device (no host arrays)")
 a = ap.parse_args()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -32,16 +34,21 @@ sc_ranks = sc
 if a.device_scene:      # the ranks build the scene on the device; the single-GPU reference below keeps the host arrays
     sc_ranks = pkg.scene.make_scene(a.scene, solver=a.solver, dt=b.params.dt, max_iter=b.params.max_iter,
                                     den_thr=b.params.density_error_threshold, div_thr=b.params.divergence_error_threshold, device_init=True)
-s = slabs.SlabSystem(sc_ranks, rank, world, torch.device("cuda", local))
+if a.rebalance >= 0:
+    os.environ["SPHK_SLAB_REBALANCE"] = str(a.rebalance)
+s = slabs.SlabSystem(sc_ranks, rank, world, torch.device("cuda", local), cut_skew=a.skew)
+cuts0 = list(s.cuts)
 states = [slabs.gather_state(s)]
 for _ in range(a.steps):
     s.step()
     states.append(slabs.gather_state(s))
 counts = [None] * world
+s._refresh_ranges()
 dist.all_gather_object(counts, (s.n_gl, s.n_own, s.n_gr, s.cuts))
 if rank == 0:
     ref = engine.SphkSystem(sc, device=torch.device("cuda", local))
-    out = {"world": world, "scene": a.scene, "solver": a.solver, "counts": counts, "steps": []}
+    out = {"world": world, "scene": a.scene, "solver": a.solver, "counts": counts, "steps": [], "cuts_initial": cuts0, "cuts_final": list(s.cuts),
+           "rebalanced": s.rebalanced, "imbalance_at_last_rebalance": s.imbalance}
     ok = True
     for k, st in enumerate(states):
         r = ref.state()
