@@ -111,9 +111,9 @@ class ClockSampler:
 
 def ncu_traffic(kernel_substring: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the density kernel, from the committed
-    `ncu --set full` capture of this round (profiles/r01/sweeps_dfsph_2m.raw.csv); None if absent."""
+    `ncu --set full` capture of this round (profiles/r02/sweeps_dfsph_2m.raw.csv); None if absent."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01", "sweeps_dfsph_2m.raw.csv")
+    path = os.path.join(ROOT, "profiles", "r02", "sweeps_dfsph_2m.raw.csv")
     if not os.path.exists(path):
         return None, None
     try:

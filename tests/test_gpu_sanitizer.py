@@ -28,7 +28,8 @@ def _sanitize(tool, solver, extra_env=None):
     env = dict(os.environ, SPHK_STEP_GRAPH="0", **(extra_env or {}))     # plain launches: the sanitizer sees every kernel
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-4000:]
-    assert "ERROR SUMMARY: 0 errors" in r.stdout, r.stdout[-4000:]
+    clean = "ERROR SUMMARY: 0 errors" in r.stdout or "RACECHECK SUMMARY: 0 hazards displayed (0 errors, 0 warnings)" in r.stdout
+    assert clean, r.stdout[-4000:]
 
 
 @pytest.mark.parametrize("solver", ["sph", "dfsph", "pbd"])
