@@ -87,7 +87,9 @@ struct sphk_ctx {
     bool simpleBuild = false;        // build the list with the generic cell walk (test reference of k_build_list)
     float skin = 0.f;                // neighbour-list skin as a fraction of R (PBD: positions move inside a step)
     bool listHasSkin = false;        // the current list was built with a skin and displacement is being tracked
-    unsigned int* dispMax = nullptr; // device: max squared displacement since the list build (float bits)
+    unsigned int* dispMax = nullptr; // device: max squared displacement since the list build (float bits; introspection)
+    unsigned char* cellFlag = nullptr; // device [cellFlagCap]: skin lists -- 1 = a particle that moved more than skin/2 since the
+    size_t cellFlagCap = 0;            // list build is in this cell or an adjacent one: the particles here walk the cells
     int tile = 0;                    // 1: tile lists -- 16-bit tile-local indices, neighbour windows staged in shared memory by
                                      // bulk copies (k_build_tile / k_sweep_tile); 0: int32 lists gathered from global memory
     int2* tileWin = nullptr;         // [tiles * 18] {first record, count} of the 9 fluid + 9 boundary windows of every tile
@@ -108,9 +110,7 @@ struct DevScene {
     const int* __restrict__ nbr;
     const int* __restrict__ cnt;
     const float* __restrict__ massRange;
-    const unsigned int* dispMax;     // non-null: skin list in use; fall back to the cell walk when *dispMax > dispLimit
-    unsigned int dispLimit;
-    float4* posBuild;                // positions at list build (skin lists)
+    const unsigned char* cellFlag;   // non-null: skin list in use; a particle whose (current) cell is flagged walks the cells
     int nF, bOff, nbrStride, kmax;
     const int2* tileWin;             // tile lists: the 18 windows of every tile (written by the list builder)
     const int* pred;                 // non-null: the kernel returns at once when *pred == 0 (device-controlled solver loops)
@@ -162,6 +162,41 @@ __device__ __forceinline__ int cell_coord(float x, float cellLength) {
 __device__ __forceinline__ int cell_index(int x, int y, int z, int3 cs) {
     return (x >= 0 && x < cs.x && y >= 0 && y < cs.y && z >= 0 && z < cs.z) ? ((x * cs.y + y) * cs.z + z)
                                                                             : (cs.x * cs.y * cs.z);
+}
+
+// ---- skin lists (PBD: positions move inside a step, PBDSolver.cu:232-256) -------------------------------------------------
+// A list built with a skin s holds every pair closer than R(1+s).  It stays complete for two particles that have EACH moved
+// less than sR/2 since the build.  A particle that moved further ("fast mover") flags its current cell and the 26 around it:
+// every particle that can be within R of it lives in one of those cells, so flagged particles -- the fast mover itself
+// included -- fall back to the exact cell walk while everybody else keeps its list.  (Round 1 used the global maximum: one
+// splashing particle sent all of them to the cell walk.)
+struct SkinTrack {
+    const float4* posBuild;      // positions at list build; nullptr: no tracking
+    unsigned int* dispMax;       // largest squared displacement seen (introspection only)
+    unsigned char* cellFlag;
+    float limit2;                // (skin/2 * R)^2
+    int3 cs, org;
+    float cellLength;
+};
+__device__ __forceinline__ int cell_coord(float x, float cellLength);
+// returns the squared displacement of particle i now at p; flags the neighbourhood of a fast mover
+__device__ __forceinline__ float skin_track(const SkinTrack& t, int i, float3 p) {
+    const float4 q = t.posBuild[i];
+    const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    if (d2 > t.limit2) {
+        const int cx = cell_coord(p.x, t.cellLength) - t.org.x, cy = cell_coord(p.y, t.cellLength) - t.org.y,
+                  cz = cell_coord(p.z, t.cellLength) - t.org.z;
+        for (int x = max(cx - 1, 0); x <= min(cx + 1, t.cs.x - 1); ++x)
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, t.cs.y - 1); ++y)
+                for (int z = max(cz - 1, 0); z <= min(cz + 1, t.cs.z - 1); ++z)
+                    t.cellFlag[(static_cast<size_t>(x) * t.cs.y + y) * t.cs.z + z] = 1;
+    }
+    return d2;
+}
+__device__ __forceinline__ void skin_track_max(const SkinTrack& t, float d2) {       // warp-wide; all lanes must call
+    for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    if ((threadIdx.x & 31) == 0 && __float_as_uint(d2) > *t.dispMax) atomicMax(t.dispMax, __float_as_uint(d2));
 }
 
 // ---- record access --------------------------------------------------------------------------------

@@ -88,6 +88,8 @@ constexpr unsigned long long kMailMagic = 0x5350484b4d41494cull;   // "SPHKMAIL"
 
 }  // namespace
 
+SkinTrack sphk_skin_track(const sphk_ctx* c, float radius, bool on);     // sphk_sweeps.cu
+
 struct sphk_mg_comm {
     int rank = 0, world = 1;
     cudaStream_t stream = nullptr;
@@ -159,8 +161,7 @@ struct HaloArgs {
     int width;               // 1 or 3
     int what;                // sphk_push_range bit mask (0: array only)
     Rec rec;
-    const float4* posBuild;  // skin tracking (PBD position halos), or nullptr
-    unsigned int* dispMax;
+    SkinTrack track;         // skin tracking (PBD position halos); track.posBuild == nullptr: off
     unsigned long long timeoutNs;
     const int* rangesDev;    // non-null: the eight plane ranges live in device memory (sphk_mg_plane_ranges); the kernel
                              // derives the slices to send and the ghost ranges from them, side[].src/ghost* hold only the
@@ -275,15 +276,12 @@ __global__ void __launch_bounds__(kHaloBlock) k_halo_mailbox(HaloArgs a) {
                 if (a.what & 1) rec_set_vel(a.rec + i, v);
                 if (a.what & 4) {
                     rec_set_pos(a.rec + i, v);
-                    if (a.posBuild) { const float3 m = v - xyz(a.posBuild[i]); d2 = fmaxf(d2, dot3(m, m)); }
+                    if (a.track.posBuild) d2 = fmaxf(d2, skin_track(a.track, i, v));
                 }
             }
         }
     }
-    if ((a.what & 4) && a.posBuild) {        // ghosts moved by their owner count against the list skin (as k_push_range)
-        for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-        if ((threadIdx.x & 31) == 0 && __float_as_uint(d2) > *a.dispMax) atomicMax(a.dispMax, __float_as_uint(d2));
-    }
+    if ((a.what & 4) && a.track.posBuild) skin_track_max(a.track, d2);   // ghosts moved by their owner count against the list skin (as k_push_range)
 }
 
 int sm_count() {
@@ -553,8 +551,7 @@ static int halo_impl(sphk_mg_comm* m, sphk_ctx* c, const sphk_scene* s, int what
     a.array = array; a.width = width; a.what = what;
     a.rec = c->rec;
     const bool track = (what & 4) && c->listHasSkin && c->listEpoch == c->searchEpoch;
-    a.posBuild = track ? c->snapA : nullptr;
-    a.dispMax = c->dispMax;
+    a.track = sphk_skin_track(c, s->radius, track);
     a.timeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
     a.rangesDev = rangesDev;
     a.capFloats = static_cast<unsigned int>(m->capFloats);

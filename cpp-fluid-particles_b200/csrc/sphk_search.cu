@@ -198,6 +198,7 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
     }
     if (e == cudaSuccess) e = dalloc(&c->massRange, 2);
     if (e == cudaSuccess) e = dalloc(&c->dispMax, 1);
+    if (e == cudaSuccess) { c->cellFlagCap = static_cast<size_t>(c->ncells) + 1; e = dalloc(&c->cellFlag, c->cellFlagCap); }
     if (e == cudaSuccess) e = dalloc(&c->tmpF, 3 * static_cast<size_t>(max_fluid));
     if (e == cudaSuccess) e = dalloc(&c->partial, 1024);
     if (e == cudaSuccess) e = dalloc(&c->loops, 2);
@@ -225,7 +226,7 @@ extern "C" int sphk_create(sphk_ctx** out, int max_fluid, int max_boundary, cons
 extern "C" void sphk_destroy(sphk_ctx* c) {
     if (!c) return;
     cudaFree(c->keys); cudaFree(c->keysSorted); cudaFree(c->idx); cudaFree(c->idxSorted);
-    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec.a); cudaFree(c->rec.b); cudaFree(c->massRange); cudaFree(c->dispMax);
+    cudaFree(c->snapA); cudaFree(c->snapB); cudaFree(c->rec.a); cudaFree(c->rec.b); cudaFree(c->massRange); cudaFree(c->dispMax); cudaFree(c->cellFlag);
     cudaFree(c->tmpF); cudaFree(c->partial); cudaFree(c->loops); cudaFree(c->cnt); cudaFree(c->nbr); cudaFree(c->cubTemp); cudaFree(c->tileWin);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
@@ -266,6 +267,13 @@ extern "C" int sphk_set_grid(sphk_ctx* c, const sphk_grid* grid) {
     c->ncells = c->cs.x * c->cs.y * c->cs.z;
     c->endBit = 1;
     while (c->endBit < 32 && (1ll << c->endBit) <= static_cast<long long>(c->ncells)) ++c->endBit;
+    if (static_cast<size_t>(c->ncells) + 1 > c->cellFlagCap) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->cellFlag);
+        c->cellFlag = nullptr;
+        c->cellFlagCap = static_cast<size_t>(c->ncells) + 1;
+        if (dalloc(&c->cellFlag, c->cellFlagCap) != cudaSuccess) { cudaGetLastError(); c->cellFlagCap = 0; return SPHK_ERR_ALLOC; }
+    }
     c->fluidSearched = false; c->boundarySearched = false; c->permValid = false;
     c->listEpoch = ~0ull; c->sTag = nullptr;
     c->actBegin = 0; c->actCount = -1; c->rangeDev = nullptr;

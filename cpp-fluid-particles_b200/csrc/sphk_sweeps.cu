@@ -240,7 +240,6 @@ struct OpBuildList {
     }
     __device__ void end(Acc& a, int i, float4 lo, float4, const DevScene& s) const {
         cnt[i] = a.n;
-        if (posBuild) posBuild[i] = lo;
         // pad the last batch with the particle itself: the self pair contributes exactly 0 to every operator
         for (int n = a.n; (n & 3) && n < s.kmax; ++n) nbr[slot(n, i, s)] = i;
     }
@@ -398,7 +397,11 @@ __device__ __forceinline__ void sweep_list_particle(const DevScene& s, const Op&
     op.begin(acc, i, lo, hi, s);
     int n = s.cnt[i];
     const float m0 = uniform_mass(s);
-    if (s.dispMax && *s.dispMax > s.dispLimit) n = s.kmax + 1;     // skin exhausted: everybody walks the cells
+    if (s.cellFlag) {                                  // skin list: a fast mover is (or was) within reach of this cell -> exact walk
+        const int c = cell_index(cell_coord(lo.x, s.cellLength) - s.org.x, cell_coord(lo.y, s.cellLength) - s.org.y,
+                                 cell_coord(lo.z, s.cellLength) - s.org.z, s.cs);
+        if (c >= s.cs.x * s.cs.y * s.cs.z || s.cellFlag[c]) n = s.kmax + 1;
+    }
     if (n <= s.kmax) {
         const int nb4 = (n + 3) >> 2;
         const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + i;
@@ -562,7 +565,6 @@ k_build_tile(const DevScene s, unsigned short* __restrict__ nbr16, int* __restri
     const bool staged = T <= SPHK_TILE_CAP;
     if (staged && T > 0) mbar_wait(&bar, 0);        // every thread: the block must not retire with bulk copies in flight
     if (!have || !in_range(s, i)) return;
-    if (posBuild) posBuild[i] = lo;
     if (!staged || c >= ncells) { cnt[i] = s.kmax + 1; return; }      // this particle walks the cells (exact fallback)
     const float3 xi = xyz(lo);
     const int zlo = max(cz - 1, 0), zhi = min(cz + 1, s.cs.z - 1);
@@ -669,7 +671,6 @@ k_build_list_staged(const DevScene s, int* __restrict__ nbr, int* __restrict__ c
     }
     cnt[i] = n;
     for (int m = n; (m & 3) && m < s.kmax; ++m) { *wp = i; ++wp; }            // pad the open batch with the particle itself
-    if (posBuild) posBuild[i] = lo;
 }
 
 // ---- sweep ----------------------------------------------------------------------------------------------------------------
@@ -714,7 +715,11 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_tile(const DevScene s, con
     op.begin(acc, i, lo, hi, s);
     int n = s.cnt[i];
     const float m0 = uniform_mass(s);
-    if (s.dispMax && *s.dispMax > s.dispLimit) n = s.kmax + 1;     // skin exhausted: everybody walks the cells
+    if (s.cellFlag) {                                  // skin list: a fast mover is (or was) within reach of this cell -> exact walk
+        const int c = cell_index(cell_coord(lo.x, s.cellLength) - s.org.x, cell_coord(lo.y, s.cellLength) - s.org.y,
+                                 cell_coord(lo.z, s.cellLength) - s.org.z, s.cs);
+        if (c >= s.cs.x * s.cs.y * s.cs.z || s.cellFlag[c]) n = s.kmax + 1;
+    }
     if (!Op::kHi && m0 < 0.f) n = s.kmax + 1;                      // non-uniform fluid masses: a sweep that stages A only has no neighbour mass
     if (n <= s.kmax && T <= SPHK_TILE_CAP) {
         const int nb8 = (n + 7) >> 3;
@@ -796,7 +801,6 @@ __device__ __forceinline__ void build_particle_global(const DevScene& s, int i, 
     cnt[i] = n;
     // pad the open batch with the particle itself: the self pair contributes exactly 0 to every operator
     for (int m = n; (m & 3) && m < s.kmax; ++m) { *wp = i; ++wp; }
-    if (posBuild) posBuild[i] = lo;
 }
 
 __global__ void __launch_bounds__(SPHK_BLOCK)
@@ -886,8 +890,7 @@ k_advect(Rec rec, float* __restrict__ pos, float* __restrict__ vel, int n, float
 }
 // thrust::transform(pos += dpos) + enforceBoundary_CUDA(pos), PBDSolver.cu:212-223,247-253
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_apply_delta_pos(Rec rec, float* __restrict__ pos, const float* __restrict__ dpos, int n, float3 space,
-                  const float4* __restrict__ posBuild, unsigned int* __restrict__ dispMax) {
+k_apply_delta_pos(Rec rec, float* __restrict__ pos, const float* __restrict__ dpos, int n, float3 space, const SkinTrack track) {
     const int i = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     float d2 = 0.f;
     if (i < n) {
@@ -896,12 +899,9 @@ k_apply_delta_pos(Rec rec, float* __restrict__ pos, const float* __restrict__ dp
         p.x += d.x; p.y += d.y; p.z += d.z;
         clamp_axis(p.x, nullptr, space.x); clamp_axis(p.y, nullptr, space.y); clamp_axis(p.z, nullptr, space.z);
         rec_set_pos(rec + i, xyz(p)); store3(pos, i, xyz(p));
-        if (posBuild) { const float3 m = xyz(p) - xyz(posBuild[i]); d2 = dot3(m, m); }
+        if (track.posBuild) d2 = skin_track(track, i, xyz(p));
     }
-    if (posBuild) {     // max squared displacement since the (skin) list was built
-        for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-        if ((threadIdx.x & 31) == 0 && __float_as_uint(d2) > *dispMax) atomicMax(dispMax, __float_as_uint(d2));
-    }
+    if (track.posBuild) skin_track_max(track, d2);
 }
 // vel = (pos - posLast) / dt, PBDSolver.cu:55-60
 __global__ void __launch_bounds__(SPHK_BLOCK)
@@ -974,8 +974,17 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
     if (c->rangeDev) { d.iBegin = 0; d.iEnd = c->nF; }      // launched over everything, cut on the device
     d.k = kernel_constants(s->radius);
     d.r2list = d.k.r2cut;
-    d.dispMax = nullptr; d.dispLimit = 0u; d.posBuild = nullptr;
+    d.cellFlag = nullptr;
     return d;
+}
+
+SkinTrack sphk_skin_track(const sphk_ctx* c, float radius, bool on) {
+    SkinTrack t;
+    const float half = 0.5f * c->skin * radius;
+    t.posBuild = on ? c->snapA : nullptr;
+    t.dispMax = c->dispMax; t.cellFlag = c->cellFlag; t.limit2 = half * half;
+    t.cs = c->cs; t.org = c->org; t.cellLength = c->cellLength;
+    return t;
 }
 
 static int ensure_list(sphk_ctx* c, const DevScene& d) {
@@ -993,6 +1002,10 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
         const float rs = d.k.R * (1.0f + c->skin);
         b.r2list = rs * rs * (1.0f + 1e-5f);
         if (cudaMemsetAsync(c->dispMax, 0, sizeof(unsigned int), c->stream) != cudaSuccess) return SPHK_ERR_STATE;
+        if (cudaMemsetAsync(c->cellFlag, 0, static_cast<size_t>(c->ncells) + 1, c->stream) != cudaSuccess) return SPHK_ERR_STATE;
+        // positions at build time of EVERY local particle (ghosts of a slab rank included: their owners move them)
+        if (cudaMemcpyAsync(c->snapA, c->rec.a, sizeof(float4) * static_cast<size_t>(c->nF), cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess)
+            return SPHK_ERR_STATE;
     }
     if (c->tile) {
         static bool attr = false;
@@ -1000,18 +1013,18 @@ static int ensure_list(sphk_ctx* c, const DevScene& d) {
         if (!attr) { cudaFuncSetAttribute(k_build_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
         const int tiles = (b.iEnd + SPHK_BLOCK - 1) / SPHK_BLOCK - b.iBegin / SPHK_BLOCK;
         k_build_tile<<<tiles, SPHK_BLOCK, smem, c->stream>>>(b, reinterpret_cast<unsigned short*>(c->nbr), c->cnt,
-                                                              c->listHasSkin ? c->snapA : nullptr, c->tileWin);
+                                                              nullptr, c->tileWin);
     } else if (c->simpleBuild) {
-        OpBuildList op{c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr};
+        OpBuildList op{c->nbr, c->cnt, nullptr};
         k_sweep_cells<OpBuildList><<<sphk_blocks(b.iEnd - b.iBegin), SPHK_BLOCK, 0, c->stream>>>(b, op);
     } else if (c->stagedBuild) {
         static bool attr = false;
         const int smem = (SPHK_BUILD_CAP + 1) * 16;
         if (!attr) { cudaFuncSetAttribute(k_build_list_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
         const int tiles = (b.iEnd + SPHK_BLOCK - 1) / SPHK_BLOCK - b.iBegin / SPHK_BLOCK;
-        k_build_list_staged<<<tiles, SPHK_BLOCK, smem, c->stream>>>(b, c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr);
+        k_build_list_staged<<<tiles, SPHK_BLOCK, smem, c->stream>>>(b, c->nbr, c->cnt, nullptr);
     } else {
-        k_build_list<<<sphk_blocks(b.iEnd - b.iBegin), SPHK_BLOCK, 0, c->stream>>>(b, c->nbr, c->cnt, c->listHasSkin ? c->snapA : nullptr);
+        k_build_list<<<sphk_blocks(b.iEnd - b.iBegin), SPHK_BLOCK, 0, c->stream>>>(b, c->nbr, c->cnt, nullptr);
     }
     c->launches++;
     c->listEpoch = c->searchEpoch;
@@ -1028,12 +1041,7 @@ template <class Op> static int run_sweep(sphk_ctx* c, const sphk_scene* s, const
         const int rc = ensure_list(c, d);
         if (rc != SPHK_OK) return rc;
         d.nbr = c->nbr;
-        if (c->listHasSkin) {
-            const float half = 0.5f * c->skin * d.k.R;
-            const float lim = half * half;
-            d.dispMax = c->dispMax;
-            memcpy(&d.dispLimit, &lim, sizeof(float));
-        }
+        if (c->listHasSkin) d.cellFlag = c->cellFlag;
         if (c->tile) {
             static bool attr = false;
             const int smem = (SPHK_TILE_CAP + 1) * 16 * (Op::kHi ? 2 : 1);
@@ -1219,7 +1227,7 @@ extern "C" int sphk_pbd_delta_pos_apply(sphk_ctx* c, const sphk_scene* s, const 
     const bool track = c->listHasSkin && c->listEpoch == c->searchEpoch;
     k_apply_delta_pos<<<sphk_blocks(c->nF), SPHK_BLOCK, 0, c->stream>>>(c->rec, s->fluid.pos, delta_pos, c->nF,
                                                                        make_float3(space[0], space[1], space[2]),
-                                                                       track ? c->snapA : nullptr, c->dispMax);
+                                                                       sphk_skin_track(c, s->radius, track));
     c->launches++;
     c->posDirty = true;
     SPHK_CUDA_TRY(cudaGetLastError());
@@ -1249,9 +1257,8 @@ extern "C" int sphk_pbd_xsph(sphk_ctx* c, const sphk_scene* s, float xc, float r
 }
 
 __global__ void __launch_bounds__(SPHK_BLOCK)
-k_push_range(Rec rec, const float* __restrict__ vel, const float* __restrict__ scalar,
-             const float* __restrict__ pos, const float4* __restrict__ posBuild, unsigned int* __restrict__ dispMax,
-             int begin, int count) {
+k_push_range(Rec rec, const float* __restrict__ vel, const float* __restrict__ scalar, const float* __restrict__ pos,
+             const SkinTrack track, int begin, int count) {
     const int t = blockIdx.x * SPHK_BLOCK + threadIdx.x;
     float d2 = 0.f;
     if (t < count) {
@@ -1261,13 +1268,10 @@ k_push_range(Rec rec, const float* __restrict__ vel, const float* __restrict__ s
         if (pos) {
             const float3 p = load3(pos, i);
             rec_set_pos(rec + i, p);
-            if (posBuild) { const float3 m = p - xyz(posBuild[i]); d2 = dot3(m, m); }
+            if (track.posBuild) d2 = skin_track(track, i, p);     // ghosts moved by their owner count like local moves do
         }
     }
-    if (pos && posBuild) {      // ghosts moved by their owner count against the skin like local moves do
-        for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-        if ((threadIdx.x & 31) == 0 && __float_as_uint(d2) > *dispMax) atomicMax(dispMax, __float_as_uint(d2));
-    }
+    if (pos && track.posBuild) skin_track_max(track, d2);
 }
 
 extern "C" int sphk_set_active_range(sphk_ctx* c, int begin, int count) {
@@ -1293,7 +1297,7 @@ extern "C" int sphk_push_range(sphk_ctx* c, const sphk_scene* s, int what, const
     const bool track = (what & 4) && c->listHasSkin && c->listEpoch == c->searchEpoch;
     k_push_range<<<sphk_blocks(count), SPHK_BLOCK, 0, c->stream>>>(c->rec, (what & 1) ? s->fluid.vel : nullptr,
                                                                   (what & 2) ? array : nullptr, (what & 4) ? s->fluid.pos : nullptr,
-                                                                  track ? c->snapA : nullptr, c->dispMax, begin, count);
+                                                                  sphk_skin_track(c, s->radius, track), begin, count);
     c->launches++;
     if (what & 4) c->posDirty = true;
     SPHK_CUDA_TRY(cudaGetLastError());
@@ -1378,6 +1382,17 @@ extern "C" int sphk_get_neighbor_list(sphk_ctx* c, const sphk_scene* s, int* cou
     if (counts_out) SPHK_CUDA_TRY(cudaMemcpyAsync(counts_out, c->cnt, sizeof(int) * static_cast<size_t>(c->nF), cudaMemcpyDeviceToDevice, c->stream));
     if (entries_out) SPHK_CUDA_TRY(cudaMemcpyAsync(entries_out, c->nbr, sizeof(int) * static_cast<size_t>(c->kmax) * c->capF,
                                                    cudaMemcpyDeviceToDevice, c->stream));
+    return SPHK_OK;
+}
+
+extern "C" int sphk_get_skin_displacement(sphk_ctx* c, float* host_out) {
+    if (!c || !host_out) return SPHK_ERR_INVALID;
+    unsigned int bits = 0;
+    SPHK_CUDA_TRY(cudaMemcpyAsync(&bits, c->dispMax, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+    SPHK_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    float d2;
+    memcpy(&d2, &bits, sizeof(d2));
+    *host_out = sqrtf(d2);
     return SPHK_OK;
 }
 

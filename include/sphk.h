@@ -317,6 +317,8 @@ int sphk_get_permutation(sphk_ctx* ctx, int* perm_out, int n);
 /* raw copy of the current neighbour list (device to device): counts int[n]; entries int[capacity*max_fluid] in
  * the int4-packed layout nbr4[(k/4)*max_fluid + i].{x,y,z,w}.  Either pointer may be NULL. */
 int sphk_get_neighbor_list(sphk_ctx* ctx, const sphk_scene* s, int* counts_out, int* entries_out);
+/* largest displacement of any particle since the skin list was built (PBD; synchronises) */
+int sphk_get_skin_displacement(sphk_ctx* ctx, float* host_out);
 /* neighbour-list statistics of the last build: host ints {max_count, overflow_particles, total} */
 int sphk_list_stats(sphk_ctx* ctx, const sphk_scene* s, long long out_host[3]);
 

@@ -289,6 +289,32 @@ def test_tile_lists_reproduce_global_lists(pkg, built, O, solver):
     a.close(); b.close()
 
 
+def test_pbd_skin_list_with_fast_movers(pkg, built, O):
+    """PBD moves particles inside a step (Q7); its neighbour list carries a skin and stays valid for particles that moved
+    less than skin/2.  A strongly jittered block makes the first projections move many particles further than that: they
+    flag their cell neighbourhood and everybody there walks the cells, the rest keeps the list.  The result must be the
+    pure cell-walk result (same pairs; equal up to the order of exact zeros / FMA contraction)."""
+    _torch()
+    import ctypes as C
+    from cpp_fluid_particles_b200 import engine
+    sc = pkg.scene.make_scene("config0", solver="pbd", dt=0.004, max_iter=4, jitter=0.006)
+    a = engine.SphkSystem(sc, step0=False)
+    b = engine.SphkSystem(sc, step0=False, use_list=False)
+    worst = 0.0
+    for k in range(6):
+        a.step(); b.step()
+        d = C.c_float()
+        a.L.sphk_get_skin_displacement(a.ctx, C.byref(d))
+        worst = max(worst, d.value / sc.params.radius)
+        sa, sb = a.state(), b.state()
+        assert np.array_equal(sa["p2c"], sb["p2c"]), f"step {k}"
+        # (a missed neighbour would show at 1e-2; 5e-6 covers the rounding of two kernel instantiations on this rough scene)
+        assert_close(sa["pos"], sb["pos"], tol=5e-6, what=f"pbd fast movers step {k} pos")
+        assert_close(sa["density"], sb["density"], tol=5e-6, what=f"pbd fast movers step {k} density")
+    assert worst > 0.075, f"the scene was meant to push particles beyond skin/2 (largest displacement {worst:.3f} R)"
+    a.close(); b.close()
+
+
 def test_list_overflow_falls_back_exactly(pkg, built, O):
     """A list capacity far below the neighbour count must not change results (per-particle cell-walk fallback)."""
     _torch()
