@@ -49,6 +49,7 @@ ALG_BYTES = {  # algorithmic HBM bytes per fluid particl
     "viscosity+surface": 76,          # viscosity 40 + surface 52 - shared pos/mass 16
     # density/alpha + colour gradient + first divergence error: R pos12 vel12 mass4, W density4 alpha4 colorGrad12 error4 stiff4
     "density_alpha+color_grad+div_error": 56,
+    "pbd_xsph+color_grad": 52,        # xsph 40 + colour gradient 28 - shared pos/mass 16
 }
 SCENE_OF_N = {1: "2m", 2: "4m", 4: "8m", 8: "16m"}
 
@@ -243,7 +244,8 @@ def timed_kernels(solver: str):
                 ("viscosity + surface (fused sweep)", "fused_viscosity_surface", "viscosity+surface")]
     if solver == "pbd":
         return [("density: pbd_density_lambda", "pbd_density_lambda", "pbd_lambda"),
-                ("pbd_delta_pos_apply", "pbd_delta_pos_apply", "pbd_delta_pos"), ("pbd_xsph", "pbd_xsph", "pbd_xsph")]
+                ("pbd_delta_pos_apply", "pbd_delta_pos_apply", "pbd_delta_pos"),
+                ("pbd_xsph + colour gradient (fused sweep)", "fused_pbd_xsph_color_grad", "pbd_xsph+color_grad"), ("surface", "surface", "surface")]
     return [("density: computeDensity + colour gradient (fused sweep)", "fused_density_color_grad", "density+color_grad"),
             ("pressure_force", "pressure_force", "pressure_force"), ("viscosity + surface (fused sweep)", "fused_viscosity_surface", "viscosity+surface")]
 

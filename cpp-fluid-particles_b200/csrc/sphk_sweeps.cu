@@ -1256,6 +1256,22 @@ extern "C" int sphk_pbd_xsph(sphk_ctx* c, const sphk_scene* s, float xc, float r
     return SPHK_OK;
 }
 
+// XSPHViscosity_CUDA (PBDSolver.cu:89-125) + computeColorGrad_CUDA (BasicSPHSolver.cu:277-330) in one pass: the colour
+// gradient depends on positions and masses only, which PBD no longer changes after its projection (PBDSolver.cu:62-66).
+extern "C" int sphk_fused_pbd_xsph_color_grad(sphk_ctx* c, const sphk_scene* s, float xc, float rho0, float* color_grad, float rhoB) {
+    SPHK_CHECK_SCENE(c, s);
+    if (!color_grad) return SPHK_ERR_INVALID;
+    float4* tmp = c->snapB;
+    OpPair<OpXsph, OpColorGrad> op{OpXsph{tmp, xc, rho0}, OpColorGrad{color_grad, rho0, rhoB}};
+    const int rc = run_sweep(c, s, op);
+    if (rc != SPHK_OK) return rc;
+    const int b = (c->actCount < 0 || c->rangeDev) ? 0 : c->actBegin, e = (c->actCount < 0 || c->rangeDev) ? c->nF : c->actBegin + c->actCount;
+    if (e > b) k_commit_vel<<<sphk_blocks(e - b), SPHK_BLOCK, 0, c->stream>>>(tmp, c->rec, s->fluid.vel, b, e, c->rangeDev);
+    c->launches++;
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
 __global__ void __launch_bounds__(SPHK_BLOCK)
 k_push_range(Rec rec, const float* __restrict__ vel, const float* __restrict__ scalar, const float* __restrict__ pos,
              const SkinTrack track, int begin, int count) {

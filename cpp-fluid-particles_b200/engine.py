@@ -288,6 +288,10 @@ class SphkOps:
         check(self.L.sphk_pbd_velocity_from_positions(self.ctx, self._s(), _ptr(self.pos_last), C.c_float(self.p.dt)),
               "sphk_pbd_velocity_from_positions")
 
+    def fused_pbd_xsph_color_grad(self):
+        check(self.L.sphk_fused_pbd_xsph_color_grad(self.ctx, self._s(), C.c_float(self.xsph_c), C.c_float(self.p.rho0), _ptr(self.buffer3),
+                                                    C.c_float(self.p.rho_boundary)), "sphk_fused_pbd_xsph_color_grad")
+
     def pbd_xsph(self):
         check(self.L.sphk_pbd_xsph(self.ctx, self._s(), C.c_float(self.xsph_c), C.c_float(self.p.rho0)), "sphk_pbd_xsph")
 
@@ -381,10 +385,15 @@ class SphkOps:
             self._run(self.pbd_density_lambda, "scalar", self.lam)
             self.pbd_delta_pos_apply(); self.sync_positions()
         self.pbd_velocity_from_positions()
-        self._run(self.pbd_xsph, "vel", split=False)
-        if self._surface_enabled():
-            self._run(self.color_grad, "array", self.buffer3)
+        if self.fused and self._surface_enabled():   # XSPH + colour gradient in one sweep, then the surface sweep
+            self._run(self.fused_pbd_xsph_color_grad, "vel", split=False)
+            self.sync_array(self.buffer3)
             self._run(self.surface, "vel")
+        else:
+            self._run(self.pbd_xsph, "vel", split=False)
+            if self._surface_enabled():
+                self._run(self.color_grad, "array", self.buffer3)
+                self._run(self.surface, "vel")
         self.gravity()
         self.copy(self.pos_last, self.fluid.pos)
         self.advect()

@@ -298,10 +298,18 @@ void PBDSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_pt
     project(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, cellSize, spaceSize, cellLength, radius, maxIter);
     check(sphk_pbd_velocity_from_positions(current_.ctx, &current_.abi, reinterpret_cast<float*>(fluidPosLast.addr()), dt),
           "sphk_pbd_velocity_from_positions");
-    diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, xSPH_c);
-    if (surfaceTensionIntensity > EPSILON || airPressure > EPSILON)
-        handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
-                      dt, surfaceTensionIntensity, airPressure);
+    const bool surface = surfaceTensionIntensity > EPSILON || airPressure > EPSILON;
+    if (fusedSweeps_ && surface) {
+        // XSPH + colour gradient in one sweep (positions are final after the projection), then the surface sweep
+        float* cg = colorGradBuffer();
+        check(sphk_fused_pbd_xsph_color_grad(current_.ctx, &current_.abi, xSPH_c, rho0, cg, rhoB), "sphk_fused_pbd_xsph_color_grad");
+        check(sphk_surface(current_.ctx, &current_.abi, cg, dt, rho0, surfaceTensionIntensity, airPressure), "sphk_surface");
+    } else {
+        diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, xSPH_c);
+        if (surface)
+            handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
+                          dt, surfaceTensionIntensity, airPressure);
+    }
     force(fluids, dt, G);
     predict(fluids, dt, spaceSize);
 }

@@ -223,6 +223,10 @@ int sphk_pbd_velocity_from_positions(sphk_ctx* ctx, const sphk_scene* s, const f
 /* XSPHViscosity_CUDA, PBDSolver.cu:89-125; Jacobi (the reference updates in place and races, Q5) */
 int sphk_pbd_xsph(sphk_ctx* ctx, const sphk_scene* s, float c, float rho0);
 
+/* XSPHViscosity_CUDA + computeColorGrad_CUDA in one pass over the neighbour list (the colour gradient reads positions and
+ * masses only, which PBD does not change after its projection) */
+int sphk_fused_pbd_xsph_color_grad(sphk_ctx* ctx, const sphk_scene* s, float c, float rho0, float* color_grad, float rho_boundary);
+
 /* Builds the per-step neighbour list now (sweeps otherwise build it lazily on first use). */
 int sphk_build_neighbor_list(sphk_ctx* ctx, const sphk_scene* s);
 

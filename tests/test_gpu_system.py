@@ -202,7 +202,7 @@ def test_against_golden_fixtures(pkg, built, solver):
     app.close()
 
 
-@pytest.mark.parametrize("solver", ["wcsph", "dfsph"])
+@pytest.mark.parametrize("solver", ["wcsph", "dfsph", "pbd"])
 def test_fused_sweeps_equal_per_launch_site_path(pkg, built, solver):
     """The fused sweeps (default) against one kernel per reference launch site: same quantities, same order of
     operations per quantity -> equal up to FMA contraction between kernel instantiations."""

@@ -25,7 +25,7 @@ sc = pkg.scene.benchmark_scene(name, solver)
 n = sc.fluid.shape[0]
 s = engine.SphkSystem(sc)
 METHODS = ["search_fluid", "build_neighbor_list", "gravity", "viscosity", "color_grad", "surface", "density", "fused_density_color_grad",
-           "fused_viscosity_surface", "fused_density_alpha_div_error", "pressure", "pressure_force", "advect", "dfsph_density_alpha", "dfsph_div_error",
+           "fused_viscosity_surface", "fused_density_alpha_div_error", "fused_pbd_xsph_color_grad", "pressure", "pressure_force", "advect", "dfsph_density_alpha", "dfsph_div_error",
            "dfsph_div_correct", "dfsph_den_error", "dfsph_den_correct", "permute", "copy", "pbd_density_lambda",
            "pbd_delta_pos_apply", "pbd_velocity_from_positions", "pbd_xsph"]
 events = defaultdict(list)
