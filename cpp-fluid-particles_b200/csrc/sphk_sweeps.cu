@@ -307,11 +307,14 @@ __device__ __forceinline__ void fetch(const DevScene& s, int j, float4& lo, floa
 // One candidate pair (i, j) with j's gathered halves.  Mass of the neighbour: the B half when it was gathered; else
 // the A half's fourth slot for a boundary neighbour (boundary records keep their mass there, their scalar is 0), the
 // uniform fluid mass for a fluid neighbour (one extra load when the fluid masses differ).
-template <class Op>
+// kUniform: the caller has established that all fluid masses equal m0 (the list walk branches on that ONCE per particle, so
+// the per-pair code of the common case carries no trace of the extra load).
+template <class Op, bool kUniform = false>
 __device__ __forceinline__ void feed_pair(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float3 xi, int j, bool isB,
                                           float4 lo, float4 hi, float m0, float3 d, float r2) {
     float mj;
     if (Op::kHi) mj = hi.w;
+    else if (kUniform) mj = isB ? lo.w : m0;
     else mj = isB ? lo.w : (m0 < 0.f ? rec_m(s.rec + j) : m0);
     lo.w = isB ? 0.0f : lo.w;
     op.pair(acc, i, j, isB, d, r2, mj, lo, hi, s);
@@ -378,13 +381,32 @@ __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_cells(const DevScene s, co
     op.end(acc, i, lo, hi, s);
 }
 
-template <class Op>
+template <class Op, bool kUniform = false>
 __device__ __forceinline__ void list_pair(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float3 xi, int j,
                                           float4 lo, float4 hi, float m0) {
     const bool isB = j >= s.bOff;
     if (Op::kFluidOnly && isB) return;
     const float3 d = xi - xyz(lo);
-    feed_pair(s, op, acc, i, xi, j, isB, lo, hi, m0, d, dot3(d, d));
+    feed_pair<Op, kUniform>(s, op, acc, i, xi, j, isB, lo, hi, m0, d, dot3(d, d));
+}
+
+template <class Op, bool kUniform>
+__device__ __forceinline__ void walk_list(const DevScene& s, const Op& op, typename Op::Acc& acc, int i, float3 xi, int n, float m0) {
+    const int nb4 = (n + 3) >> 2;
+    const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + i;
+    int4 jn = make_int4(i, i, i, i);
+    if (nb4 > 0) jn = __ldcs(row);
+    for (int b = 0; b < nb4; ++b) {
+        const int4 j4 = jn;
+        row += s.nbrStride;
+        if (b + 1 < nb4) jn = __ldcs(row);
+        float4 l0, h0, l1, h1, l2, h2, l3, h3;
+        fetch<Op>(s, j4.x, l0, h0); fetch<Op>(s, j4.y, l1, h1); fetch<Op>(s, j4.z, l2, h2); fetch<Op>(s, j4.w, l3, h3);
+        list_pair<Op, kUniform>(s, op, acc, i, xi, j4.x, l0, h0, m0);
+        list_pair<Op, kUniform>(s, op, acc, i, xi, j4.y, l1, h1, m0);
+        list_pair<Op, kUniform>(s, op, acc, i, xi, j4.z, l2, h2, m0);
+        list_pair<Op, kUniform>(s, op, acc, i, xi, j4.w, l3, h3, m0);
+    }
 }
 
 // one particle's walk of its neighbour list (thread per particle)
@@ -403,21 +425,9 @@ __device__ __forceinline__ void sweep_list_particle(const DevScene& s, const Op&
         if (c >= s.cs.x * s.cs.y * s.cs.z || s.cellFlag[c]) n = s.kmax + 1;
     }
     if (n <= s.kmax) {
-        const int nb4 = (n + 3) >> 2;
-        const int4* __restrict__ row = reinterpret_cast<const int4*>(s.nbr) + i;
-        int4 jn = make_int4(i, i, i, i);
-        if (nb4 > 0) jn = __ldcs(row);
-        for (int b = 0; b < nb4; ++b) {
-            const int4 j4 = jn;
-            row += s.nbrStride;
-            if (b + 1 < nb4) jn = __ldcs(row);
-            float4 l0, h0, l1, h1, l2, h2, l3, h3;
-            fetch<Op>(s, j4.x, l0, h0); fetch<Op>(s, j4.y, l1, h1); fetch<Op>(s, j4.z, l2, h2); fetch<Op>(s, j4.w, l3, h3);
-            list_pair(s, op, acc, i, xi, j4.x, l0, h0, m0);
-            list_pair(s, op, acc, i, xi, j4.y, l1, h1, m0);
-            list_pair(s, op, acc, i, xi, j4.z, l2, h2, m0);
-            list_pair(s, op, acc, i, xi, j4.w, l3, h3, m0);
-        }
+        // (the warp-uniform branch keeps the common case -- equal fluid masses, SPHSystem.cu:73 -- free of the per-pair mass load)
+        if (Op::kHi || m0 >= 0.f) walk_list<Op, true>(s, op, acc, i, xi, n, m0);
+        else walk_list<Op, false>(s, op, acc, i, xi, n, m0);
     } else {
         walk_cells(s, op, acc, i, lo, m0);  // more neighbours than the list keeps: exact fallback
     }
