@@ -13,16 +13,21 @@ Printed JSON (one line, rank 0):
   value       whole-job particle-steps/s, state resident in HBM, timed on the device with CUDA events over
               exactly K steps (barrier + synchronize on both sides, max over ranks)
   e2e         the same metric through the reference-facing C++ class API (SPHSystem via the sph_app facade)
-              with HOST buffers: every step uploads pos+vel from pinned host memory, steps, and reads
-              pos+vel+density back; host<->device copies inside the timed region
+              with HOST buffers: every step takes pos+vel from pinned host memory, steps, and delivers
+              pos+vel+density to pinned host memory; all copies inside the timed region, pipelined against the
+              previous batch's step (sph_app_submit / sph_app_wait); the blocking variant is reported beside it
   roofline    the density kernel named by BASELINE.json's metric (for DFSPH: computeDensityAlpha's
-              replacement), timed live with CUDA events inside the timed region; algorithmic bytes per
+              replacement, fused with the colour gradient and the first divergence error), timed live with
+              CUDA events inside the timed region; algorithmic bytes per
               particle from SURVEY.md 8(d); peak from MEASURED_PEAKS.json; `kernels` lists every sweep timed
-  cpu_baseline  the CPU restatement (oracle/, OpenMP, all host cores) on a bounded sample of the workload
+  cpu_baseline  the CPU restatement (oracle/, OpenMP, all host cores): one warm-up + >= 3 timed steps of the
+              workload's own scene (median)
   clocks      nvidia-smi samples taken during the timed region
 --impl reference: the UNMODIFIED reference CUDA sources compiled for sm_100 (oracle/_ref/libsphref.so),
 driven through the very same facade source -- the "reference build" of the north star -- on the same
-scene; if that library is absent, the CPU restatement is timed instead (kind "port").
+scene, timed as the median of per-step wall times (its own cudaEvent figure is reported beside it); if that
+library is absent, the CPU restatement is timed instead (kind "port").
+N>1: every line is self-checked first (slabs.parity_check: two steps against a single-GPU run of the same scene).
 """
 from __future__ import annotations
 
