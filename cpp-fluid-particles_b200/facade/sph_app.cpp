@@ -28,7 +28,7 @@ struct sph_batch {
     float3* dIn[2] = {nullptr, nullptr};     // device staging: pos, vel of the batch
     float3* dOut[2] = {nullptr, nullptr};    // device staging of the result: pos, vel
     float* dOutDensity = nullptr;
-    cudaEvent_t uploaded = nullptr, computed = nullptr;
+    cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr;
     float* hPos = nullptr; float* hVel = nullptr; float* hDensity = nullptr;   // where the result goes (host)
     bool pending = false;                    // uploaded, not yet stepped
     float ms = 0.f;
@@ -37,19 +37,21 @@ struct sph_batch {
 struct sph_app {
     std::shared_ptr<SPHSystem> system;
     BaseSolver* solver = nullptr;            // owned by `system` (its constructor moves the caller's shared_ptr)
-    // pipelined path (created on first sph_app_submit)
-    cudaStream_t copyStream = nullptr;
+    // pipelined path (created on first sph_app_submit): uploads and downloads on their own streams (PCIe is full duplex)
+    cudaStream_t copyStream = nullptr, downStream = nullptr;
     sph_batch batch[2];
     unsigned long long submitted = 0;
     bool pipeReady = false;
     ~sph_app() {
         if (pipeReady) {
             cudaStreamSynchronize(copyStream);
+            cudaStreamSynchronize(downStream);
             for (auto& b : batch) {
                 cudaFree(b.dIn[0]); cudaFree(b.dIn[1]); cudaFree(b.dOut[0]); cudaFree(b.dOut[1]); cudaFree(b.dOutDensity);
-                cudaEventDestroy(b.uploaded); cudaEventDestroy(b.computed);
+                cudaEventDestroy(b.uploaded); cudaEventDestroy(b.computed); cudaEventDestroy(b.downloaded);
             }
             cudaStreamDestroy(copyStream);
+            cudaStreamDestroy(downStream);
         }
     }
 };
@@ -154,6 +156,7 @@ static bool pipe_init(sph_app* app) {
     if (app->pipeReady) return true;
     const size_t n = app->system->getFluids()->size();
     if (cudaStreamCreateWithFlags(&app->copyStream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&app->downStream, cudaStreamNonBlocking) != cudaSuccess) return false;
     for (auto& b : app->batch) {
         bool ok = true;
         for (int k = 0; k < 2; ++k) {
@@ -163,6 +166,8 @@ static bool pipe_init(sph_app* app) {
         ok = ok && cudaMalloc(reinterpret_cast<void**>(&b.dOutDensity), n * sizeof(float)) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&b.uploaded, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&b.computed, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&b.downloaded, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventRecord(b.downloaded, app->downStream) == cudaSuccess;      // "nothing to wait for" before the first use
         if (!ok) return false;
     }
     app->pipeReady = true;
@@ -182,14 +187,16 @@ static int pipe_run(sph_app* app, int slot) {
     bad |= cudaMemcpyAsync(f->getPosPtr(), b.dIn[0], n * sizeof(float3), cudaMemcpyDeviceToDevice, nullptr) != cudaSuccess;
     bad |= cudaMemcpyAsync(f->getVelPtr(), b.dIn[1], n * sizeof(float3), cudaMemcpyDeviceToDevice, nullptr) != cudaSuccess;
     b.ms = app->system->step();
+    bad |= cudaStreamWaitEvent(nullptr, b.downloaded, 0) != cudaSuccess;     // this slot's previous result has left the staging buffers
     bad |= cudaMemcpyAsync(b.dOut[0], f->getPosPtr(), n * sizeof(float3), cudaMemcpyDeviceToDevice, nullptr) != cudaSuccess;
     bad |= cudaMemcpyAsync(b.dOut[1], f->getVelPtr(), n * sizeof(float3), cudaMemcpyDeviceToDevice, nullptr) != cudaSuccess;
     bad |= cudaMemcpyAsync(b.dOutDensity, f->getDensityPtr(), n * sizeof(float), cudaMemcpyDeviceToDevice, nullptr) != cudaSuccess;
     bad |= cudaEventRecord(b.computed, nullptr) != cudaSuccess;
-    bad |= cudaStreamWaitEvent(app->copyStream, b.computed, 0) != cudaSuccess;
-    if (b.hPos) bad |= cudaMemcpyAsync(b.hPos, b.dOut[0], n * sizeof(float3), cudaMemcpyDeviceToHost, app->copyStream) != cudaSuccess;
-    if (b.hVel) bad |= cudaMemcpyAsync(b.hVel, b.dOut[1], n * sizeof(float3), cudaMemcpyDeviceToHost, app->copyStream) != cudaSuccess;
-    if (b.hDensity) bad |= cudaMemcpyAsync(b.hDensity, b.dOutDensity, n * sizeof(float), cudaMemcpyDeviceToHost, app->copyStream) != cudaSuccess;
+    bad |= cudaStreamWaitEvent(app->downStream, b.computed, 0) != cudaSuccess;
+    if (b.hPos) bad |= cudaMemcpyAsync(b.hPos, b.dOut[0], n * sizeof(float3), cudaMemcpyDeviceToHost, app->downStream) != cudaSuccess;
+    if (b.hVel) bad |= cudaMemcpyAsync(b.hVel, b.dOut[1], n * sizeof(float3), cudaMemcpyDeviceToHost, app->downStream) != cudaSuccess;
+    if (b.hDensity) bad |= cudaMemcpyAsync(b.hDensity, b.dOutDensity, n * sizeof(float), cudaMemcpyDeviceToHost, app->downStream) != cudaSuccess;
+    bad |= cudaEventRecord(b.downloaded, app->downStream) != cudaSuccess;
     b.pending = false;
     return bad;
 }
@@ -201,9 +208,8 @@ extern "C" int sph_app_submit(sph_app* app, const float* pos_in, const float* ve
     const int slot = static_cast<int>(app->submitted & 1ull);
     sph_batch& b = app->batch[slot];
     int bad = 0;
-    // (the slot's previous batch was stepped during the previous submit; its staging is free once that step has run.
-    // Its download reads dOut, which this batch overwrites only after ITS step -- two submits later on this slot --
-    // and the copy stream is in order, so the earlier download is complete by then.)
+    // (the slot's previous batch was stepped during the previous submit, so its input staging is free; its download reads
+    // the output staging, which this batch overwrites only after ITS step and after waiting for the `downloaded` event)
     bad |= cudaMemcpyAsync(b.dIn[0], pos_in, n * sizeof(float3), cudaMemcpyHostToDevice, app->copyStream) != cudaSuccess;
     bad |= cudaMemcpyAsync(b.dIn[1], vel_in, n * sizeof(float3), cudaMemcpyHostToDevice, app->copyStream) != cudaSuccess;
     bad |= cudaEventRecord(b.uploaded, app->copyStream) != cudaSuccess;
@@ -222,6 +228,7 @@ extern "C" int sph_app_wait(sph_app* app) {
     bad |= pipe_run(app, last ^ 1);
     bad |= pipe_run(app, last);
     bad |= cudaStreamSynchronize(app->copyStream) != cudaSuccess;
+    bad |= cudaStreamSynchronize(app->downStream) != cudaSuccess;
     return bad;
 }
 
