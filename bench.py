@@ -402,7 +402,9 @@ def run_ours_single(args, pkg) -> dict:
             "config": {"workload": workload_name(scene_name, solver), "n_fluid": n, "n_boundary": int(sc.boundary.shape[0]),
                        "cells": list(sc.params.cell_size), "l2": "inputs larger than L2: packed particles + neighbour list "
                        "working set per sweep is ~%d MB > 126 MB L2; no flush between steps" % int(n * (32 + 36 * 4) / 1e6),
-                       "parallelism": "1 GPU"},
+                       "parallelism": "1 GPU",
+                       "value_api": "python mirror of the C++ class layer (engine.SphkSystem: the same C-ABI calls in the same order, "
+                                    "bit-identical by test_python_mirror_equals_class_layer); e2e runs through the C++ classes"},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "clocks": clocks}
 
 

@@ -1,23 +1,24 @@
 // sphk_sweeps.cu -- the per-particle neighbour sweeps of the three solvers + element-wise steps.
 //
 // One generic sweep driver, instantiated per operator:
-//   * k_sweep_cells<Op> : walks the 27 neighbour cells in the reference's order (x outermost, z innermost;
-//     inside a cell first the fluid range, then the boundary range -- SURVEY 2.2).
-//   * k_sweep_list<Op>  : walks a per-step neighbour list (built once per neighbour search by the same cell
-//     walk, candidates kept in the reference's order) while positions are unchanged -- the ~85% of candidate
-//     pairs outside the support are tested once per step instead of once per sweep (DFSPH runs 23 sweeps per
-//     step on identical positions).
-// Data path (measured with ncu, profiles/): the sweeps are bound by L1 gather requests (one tag-stage cycle
-// per distinct 128-byte line) and by FP32 issue, not by HBM.  Hence:
-//   - a neighbour is ONE 32-byte record {x,y,z,m, vx,vy,vz,s} fetched with ONE 256-bit load (LDG.E.256);
-//     operators that need only position+mass fetch the first half (LDG.E.128);
-//   - list indices arrive four at a time in one coalesced, streaming (evict-first) 16-byte load, the next
-//     batch is prefetched, and the four dependent record gathers are issued back to back before any math;
-//   - accumulation is in registers (the reference accumulates density in global memory,
-//     BasicSPHSolver.cu:37,48); kernel constants are folded per launch; selects instead of branches.
-// The candidate ORDER is the reference's in both drivers, so sums are formed in the reference's order;
-// results agree with the reference kernels to ~1e-6 relative (tests/, <= 1e-5 required).
-// Compiled with -use_fast_math like the reference (Q10).
+//   * k_sweep_cells<Op> : walks the 27 neighbour cells row by row: the three z-neighbours of a (dx,dy) row are consecutive
+//     cell indices, hence ONE contiguous particle range per row; rows in the reference's order (dx outermost), inside a
+//     row first the fluid range, then the boundary range.  (The reference interleaves fluid and boundary per CELL,
+//     the difference is the position of a few boundary terms inside a sum, ~1e-7 relative.)
+//   * k_sweep_list<Op>  : walks a per-step neighbour list (built once per neighbour search by the same row walk, candidates
+//     kept in that order) while positions are unchanged -- the ~85% of candidate pairs outside the support are tested once
+//     per step instead of once per sweep (DFSPH runs 20 sweeps per step on identical positions).
+//   * k_sweep_tile<Op>  : the same over tile lists (neighbour windows staged in shared memory by bulk copies; option).
+// Data path (measured, DESIGN.md 4.1, profiles/r02): the sweeps are bound by the gather path -- L1 misses on scattered
+// 16-byte records -- and, for the 16-byte sweeps, increasingly by FP32 issue; not by HBM.  Hence:
+//   - a neighbour is two 16-byte halves in two arrays, A = {x,y,z,s} and B = {vx,vy,vz,m}; operators that need only
+//     position + scalar gather A (one LDG.E.128), the others A and B;
+//   - list indices arrive four at a time in one coalesced, streaming (evict-first) 16-byte load, the next batch is prefetched;
+//   - accumulation is in registers (the reference accumulates density in global memory, BasicSPHSolver.cu:37,48); kernel
+//     constants are folded per launch; selects instead of branches; the non-uniform-mass case sits behind one warp-uniform
+//     branch per particle.
+// Sums are formed row by row in the candidate order above; results agree with the reference kernels to ~1e-6 relative
+// (tests/, <= 1e-5 required).  Compiled with -use_fast_math like the reference (Q10).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
