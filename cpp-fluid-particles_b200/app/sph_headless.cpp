@@ -8,9 +8,13 @@
 // (positions, densities and the generate_dots colours of vbo.cu:26-51) for offline viewing.
 //
 //   sph_headless [--solver sph|dfsph|pbd] [--frames N] [--box L | --box LX LY LZ] [--block NX NY NZ] [--origin X Y Z]
-//                [--dt DT] [--iters K] [--dump PREFIX] [--quiet] [--emit-scene PREFIX]
+//                [--dt DT] [--iters K] [--dump PREFIX] [--quiet] [--emit-scene PREFIX] [--ranks N [--rank R --rendezvous DIR]]
 // --emit-scene writes the generated scene (PREFIX.fluid.f32, PREFIX.boundary.f32) and exits: needs no GPU, lets a
 // test compare this generator with the python one the benchmarks use.
+// --ranks N runs the same scene on N GPUs through SlabSPHSystem (host/sph_slab.hpp: the class API sharded by x-slabs):
+// without --rank the process forks one child per GPU (rank r on device r) and a fresh rendezvous directory; with
+// --rank R --rendezvous DIR it IS rank R (an external launcher's job).  Every rank dumps the particles it owns
+// (PREFIX.rank<R>.*) and prints its own summary line.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +22,11 @@
 #include <memory>
 #include <string>
 #include <vector>
+
+#include <sys/prctl.h>
+#include <sys/wait.h>
+#include <csignal>
+#include <unistd.h>
 
 #include <cuda_runtime.h>
 
@@ -29,6 +38,7 @@
 #include "Particles.h"
 #include "SPHParticles.h"
 #include "SPHSystem.h"
+#include "SlabSPHSystem.h"
 
 namespace {
 
@@ -42,6 +52,8 @@ struct Options {
     int iters = 0;                            // > 0: fixed iteration count (DFSPH thresholds -1, Q11)
     std::string dump, emitScene;
     bool quiet = false;
+    int ranks = 1, rank = -1;                 // --ranks N: SlabSPHSystem on N GPUs; --rank R: this process is rank R
+    std::string rendezvous;
 };
 
 bool parse(int argc, char** argv, Options& o) {
@@ -55,6 +67,9 @@ bool parse(int argc, char** argv, Options& o) {
         else if (a == "--dump" && need(i, 1)) o.dump = argv[++i];
         else if (a == "--emit-scene" && need(i, 1)) o.emitScene = argv[++i];
         else if (a == "--quiet") o.quiet = true;
+        else if (a == "--ranks" && need(i, 1)) o.ranks = std::atoi(argv[++i]);
+        else if (a == "--rank" && need(i, 1)) o.rank = std::atoi(argv[++i]);
+        else if (a == "--rendezvous" && need(i, 1)) o.rendezvous = argv[++i];
         else if (a == "--block" && need(i, 3)) { for (int k = 0; k < 3; ++k) o.block[k] = std::atoi(argv[++i]); }
         else if (a == "--origin" && need(i, 3)) { for (int k = 0; k < 3; ++k) o.origin[k] = static_cast<float>(std::atof(argv[++i])); }
         else if (a == "--box" && need(i, 1)) {
@@ -70,6 +85,7 @@ bool parse(int argc, char** argv, Options& o) {
             return false;
         }
     }
+    if (o.ranks < 1 || o.rank >= o.ranks || (o.rank >= 0 && o.ranks > 1 && o.rendezvous.empty())) return false;
     return o.frames >= 0 && o.block[0] > 0 && o.block[1] > 0 && o.block[2] > 0 &&
            (o.solver == "sph" || o.solver == "wcsph" || o.solver == "dfsph" || o.solver == "pbd");
 }
@@ -125,7 +141,8 @@ int main(int argc, char** argv) {
     Options o;
     if (!parse(argc, argv, o)) {
         std::fprintf(stderr, "usage: sph_headless [--solver sph|dfsph|pbd] [--frames N] [--box L | LX LY LZ] [--block NX NY NZ] "
-                             "[--origin X Y Z] [--dt DT] [--iters K] [--dump PREFIX] [--quiet] [--emit-scene PREFIX]\n");
+                             "[--origin X Y Z] [--dt DT] [--iters K] [--dump PREFIX] [--quiet] [--emit-scene PREFIX] "
+                             "[--ranks N [--rank R --rendezvous DIR]]\n");
         return 2;
     }
     // ---- scene constants, main.cpp:54-67 ----
@@ -141,10 +158,44 @@ int main(int argc, char** argv) {
         std::printf("{\"cells\": [%d, %d, %d]}\n", cells.x, cells.y, cells.z);
         return ok ? 0 : 5;
     }
+    // ---- --ranks N without --rank: one child per GPU, forked BEFORE the first CUDA call of this process ----
+    if (o.ranks > 1 && o.rank < 0) {
+        char tmpl[] = "/tmp/sph_headless_rdv_XXXXXX";
+        if (!mkdtemp(tmpl)) { std::perror("sph_headless: mkdtemp"); return 5; }
+        o.rendezvous = tmpl;
+        std::vector<pid_t> kids;
+        for (int r = 0; r < o.ranks; ++r) {
+            std::fflush(nullptr);
+            const pid_t pid = fork();
+            if (pid < 0) { std::perror("sph_headless: fork"); return 5; }
+            if (pid == 0) { prctl(PR_SET_PDEATHSIG, SIGKILL); o.rank = r; kids.clear(); break; }   // never outlive the launcher
+            kids.push_back(pid);
+        }
+        if (o.rank < 0) {
+            int worstRc = 0;
+            for (const pid_t pid : kids) {
+                int st = 0;
+                waitpid(pid, &st, 0);
+                const int rc = WIFEXITED(st) ? WEXITSTATUS(st) : 128;
+                worstRc = rc > worstRc ? rc : worstRc;
+            }
+            for (const char* f : {"nccl_id"}) std::remove((o.rendezvous + "/" + f).c_str());
+            for (int r = 0; r < o.ranks; ++r)
+                for (const char* f : {"ipc_", "connected_"}) std::remove((o.rendezvous + "/" + f + std::to_string(r)).c_str());
+            rmdir(o.rendezvous.c_str());
+            return worstRc;
+        }
+    }
+    const bool slab = o.ranks > 1;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         std::fprintf(stderr, "sph_headless: no CUDA device -- this engine has no CPU path\n");
         return 3;
+    }
+    if (slab) {
+        if (ndev < o.ranks) { std::fprintf(stderr, "sph_headless: --ranks %d needs %d GPUs, this box has %d\n", o.ranks, o.ranks, ndev); return 3; }
+        if (cudaSetDevice(o.rank) != cudaSuccess) { std::fprintf(stderr, "sph_headless: cudaSetDevice(%d) failed\n", o.rank); return 3; }
+        o.quiet = o.quiet || o.rank != 0;
     }
     const bool wcsph = (o.solver == "sph" || o.solver == "wcsph");
     const float dt = o.dt > 0.0f ? o.dt : (wcsph ? 0.001f : 0.004f);
@@ -170,9 +221,20 @@ int main(int argc, char** argv) {
         pSolver = o.iters > 0 ? std::make_shared<DFSPHSolver>(nFluid, -1.0f, -1.0f, o.iters) : std::make_shared<DFSPHSolver>(nFluid);
     else
         pSolver = std::make_shared<BasicSPHSolver>(nFluid);
-    auto pSystem = std::make_shared<SPHSystem>(fluidParticles, boundaryParticles, pSolver, spaceSize, sphCellLength, sphSmoothingRadius,
-                                               dt, sphM0, sphRho0, sphRhoBoundary, sphStiff, sphVisc, sphSurfaceTensionIntensity,
-                                               sphAirPressure, sphG, cellSize);
+    std::shared_ptr<SPHSystem> pSystem;
+    std::shared_ptr<SlabSPHSystem> pSlab;
+    if (slab) {
+        sphb200::SlabBootstrap boot;
+        boot.rank = o.rank; boot.world = o.ranks; boot.rendezvousDir = o.rendezvous;
+        pSlab = std::make_shared<SlabSPHSystem>(fluidParticles, boundaryParticles, pSolver, spaceSize, sphCellLength, sphSmoothingRadius,
+                                                dt, sphM0, sphRho0, sphRhoBoundary, sphStiff, sphVisc, sphSurfaceTensionIntensity,
+                                                sphAirPressure, sphG, cellSize, boot);
+        if (!pSlab->ok()) { std::fprintf(stderr, "sph_headless: rank %d: SlabSPHSystem did not come up\n", o.rank); return 4; }
+    } else {
+        pSystem = std::make_shared<SPHSystem>(fluidParticles, boundaryParticles, pSolver, spaceSize, sphCellLength, sphSmoothingRadius,
+                                              dt, sphM0, sphRho0, sphRhoBoundary, sphStiff, sphVisc, sphSurfaceTensionIntensity,
+                                              sphAirPressure, sphG, cellSize);
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) {
         std::fprintf(stderr, "sph_headless: %s\n", cudaGetErrorString(cudaGetLastError()));
         return 4;
@@ -183,7 +245,7 @@ int main(int argc, char** argv) {
     float totalTime = 0.0f, worst = 0.0f;
     for (; frameId < o.frames;) {
         ++frameId;
-        const auto milliseconds = pSystem->step();
+        const auto milliseconds = slab ? pSlab->step() : pSystem->step();
         totalTime += milliseconds;
         worst = milliseconds > worst ? milliseconds : worst;
         if (!o.quiet)
@@ -193,7 +255,17 @@ int main(int argc, char** argv) {
     if (!o.quiet) std::printf("\n");
 
     // ---- optional dump through the public accessors + the render hook (vbo.cu:46-51) ----
-    if (!o.dump.empty()) {
+    if (!o.dump.empty() && slab) {
+        // the particles this rank owns: [ownedBegin, ownedBegin + size) of the local set
+        const auto fluids = pSlab->getFluids();
+        const size_t n = static_cast<size_t>(pSlab->size()), b = static_cast<size_t>(pSlab->ownedBegin());
+        std::vector<float> pos(3 * n), den(n);
+        const bool ok = cudaMemcpy(pos.data(), fluids->getPosPtr() + b, n * sizeof(float3), cudaMemcpyDeviceToHost) == cudaSuccess &&
+                        cudaMemcpy(den.data(), fluids->getDensityPtr() + b, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess &&
+                        write_floats(o.dump + ".rank" + std::to_string(o.rank) + ".pos.f32", pos) &&
+                        write_floats(o.dump + ".rank" + std::to_string(o.rank) + ".density.f32", den);
+        if (!ok) { std::fprintf(stderr, "sph_headless: dump to '%s.rank%d.*' failed\n", o.dump.c_str(), o.rank); return 5; }
+    } else if (!o.dump.empty()) {
         const auto fluids = pSystem->getFluids();
         const size_t n = fluids->size();
         std::vector<float> pos(3 * n), den(n), col(3 * n);
@@ -210,6 +282,13 @@ int main(int argc, char** argv) {
         if (!ok) { std::fprintf(stderr, "sph_headless: dump to '%s.*' failed\n", o.dump.c_str()); return 5; }
     }
     const float avg = frameId ? totalTime / float(frameId) : 0.0f;
+    if (slab) {
+        std::printf("{\"solver\": \"%s\", \"rank\": %d, \"ranks\": %d, \"n_fluid\": %d, \"n_owned\": %d, \"halo\": \"%s\", \"dt\": %g, "
+                    "\"frames\": %d, \"avg_ms_per_frame\": %.4f, \"max_ms_per_frame\": %.4f}\n",
+                    o.solver.c_str(), o.rank, o.ranks, nFluid, pSlab->size(), pSlab->haloTransport(), dt, frameId, avg, worst);
+        std::fflush(stdout);
+        return 0;
+    }
     std::printf("{\"solver\": \"%s\", \"n_fluid\": %d, \"n_boundary\": %d, \"cells\": [%d, %d, %d], \"dt\": %g, \"frames\": %d, "
                 "\"avg_ms_per_frame\": %.4f, \"max_ms_per_frame\": %.4f, \"particle_steps_per_s\": %.1f}\n",
                 o.solver.c_str(), nFluid, nBoundary, cellSize.x, cellSize.y, cellSize.z, dt, frameId, avg, worst,

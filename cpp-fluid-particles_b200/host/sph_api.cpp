@@ -13,14 +13,14 @@ using sphb200::check;
 // Engine
 // ================================================================================================
 namespace sphb200 {
-Engine::Engine(int maxFluid, int maxBoundary, int3 cellSize, float cellLength) {
+Engine::Engine(int maxFluid, int maxBoundary, int3 cellSize, float cellLength, int3 origin) {
     // blocking stream: legacy-default-stream work of the caller (DArray memset, cudaMemcpy through the
     // raw accessors) orders with the engine's work exactly as it does in the single-stream reference
     CUDA_CALL(cudaStreamCreate(&stream_));
     sphk_grid g;
     g.cell_size[0] = cellSize.x; g.cell_size[1] = cellSize.y; g.cell_size[2] = cellSize.z;
     g.cell_length = cellLength;
-    g.origin[0] = g.origin[1] = g.origin[2] = 0;
+    g.origin[0] = origin.x; g.origin[1] = origin.y; g.origin[2] = origin.z;
     const int rc = sphk_create(&ctx_, maxFluid, maxBoundary, &g, stream_);
     if (rc != 0) {
         // no CPU fallback: a missing device / failed allocation is reported and leaves the system inert
@@ -87,11 +87,15 @@ void BasicSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shar
         // density and the colour gradient depend on positions and masses only: one sweep computes both (the
         // reference computes them in two sweeps, :277-330 and :32-83, with nothing in between that they read)
         densityAndColorGrad(nullptr, rho0, rhoB, surface);
+        if (surface) produced(0, colorGradBuffer(), 3);
         diffuseAndSurface(rho0, rhoB, visc, dt, surfaceTensionIntensity, airPressure, surface, true);
+        producedVel(fluids);
         check(sphk_pressure(current_.ctx, &current_.abi, rho0, stiff), "sphk_pressure");
+        produced(0, fluids->getDensityPtr(), 1); produced(0, fluids->getPressurePtr(), 1);
         check(sphk_pressure_force(current_.ctx, &current_.abi, dt), "sphk_pressure_force");
     } else {
         diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, visc, dt);
+        producedVel(fluids);
         if (surface)
             handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
                           dt, surfaceTensionIntensity, airPressure);
@@ -145,6 +149,7 @@ void BasicSPHSolver::project(std::shared_ptr<SPHParticles>&, const std::shared_p
     if (!current_.ctx) return;
     check(sphk_density(current_.ctx, &current_.abi), "sphk_density");
     check(sphk_pressure(current_.ctx, &current_.abi, rho0, stiff), "sphk_pressure");
+    produced(0, current_.abi.fluid.density, 1); produced(0, current_.abi.fluid.pressure, 1);
     check(sphk_pressure_force(current_.ctx, &current_.abi, dt), "sphk_pressure_force");
 }
 
@@ -163,7 +168,9 @@ void BasicSPHSolver::handleSurface(std::shared_ptr<SPHParticles>&, const std::sh
     if (!current_.ctx) return;
     float* cg = reinterpret_cast<float*>(bufferFloat3.addr());
     check(sphk_color_grad(current_.ctx, &current_.abi, cg, rho0, rhoB), "sphk_color_grad");
+    produced(0, cg, 3);
     check(sphk_surface(current_.ctx, &current_.abi, cg, dt, rho0, surfaceTensionIntensity, airPressure), "sphk_surface");
+    produced(1, current_.abi.fluid.vel, 3);
 }
 
 // ================================================================================================
@@ -182,6 +189,8 @@ void DFSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_
         check(sphk_fused_dfsph_density_alpha_div_error(current_.ctx, &current_.abi, alpha.addr(), surface ? colorGradBuffer() : nullptr,
                                                        rho0, rhoB, error.addr(), bufferFloat.addr(), dt),
               "sphk_fused_dfsph_density_alpha_div_error");
+        produced(2, bufferFloat.addr(), 1);
+        if (surface) produced(0, colorGradBuffer(), 3);
     } else {
         check(sphk_dfsph_density_alpha(current_.ctx, &current_.abi, alpha.addr()), "sphk_dfsph_density_alpha");
     }
@@ -189,8 +198,10 @@ void DFSPHSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_
     force(fluids, dt, G);
     if (fusedSweeps_) {
         diffuseAndSurface(rho0, rhoB, visc, dt, surfaceTensionIntensity, airPressure, surface, true);
+        producedVel(fluids);
     } else {
         BasicSPHSolver::diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, visc, dt);
+        producedVel(fluids);
         if (surface)
             handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
                           dt, surfaceTensionIntensity, airPressure);
@@ -207,10 +218,13 @@ int DFSPHSolver::correctDivergenceError(float rho0, float dt, float errorThresho
     auto totalError = std::numeric_limits<float>::max();
     auto iter = 0;
     sphk_ctx* ctx = current_.ctx;
-    if (!firstErrorDone)
+    if (!firstErrorDone) {
         check(sphk_dfsph_div_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0),
               "sphk_dfsph_div_error");
-    if (errorThreshold >= 0.0f && deviceLoops_) {
+        produced(2, bufferFloat.addr(), 1);
+    }
+    const float thresholdCount = static_cast<float>(globalCount_ >= 0 ? globalCount_ : num);
+    if (errorThreshold >= 0.0f && deviceLoops_ && !fieldHook_) {
         // the loop test runs on the device: maxIter bodies are enqueued, the ones after convergence return at once
         check(sphk_loop_begin(ctx, 0, 1, maxIter_, errorThreshold * num * rho0, 1), "sphk_loop_begin");
         for (int k = 0; k < maxIter_; ++k) {
@@ -222,12 +236,14 @@ int DFSPHSolver::correctDivergenceError(float rho0, float dt, float errorThresho
         check(sphk_loop_end(ctx, 0), "sphk_loop_end");
         return -1;      // known on the device; lastDivergenceIterations() reads it back
     }
-    while ((iter < 1 || totalError > errorThreshold * num * rho0) && iter < maxIter_) {
+    while ((iter < 1 || totalError > errorThreshold * thresholdCount * rho0) && iter < maxIter_) {
         check(sphk_dfsph_div_correct(ctx, &current_.abi, bufferFloat.addr()), "sphk_dfsph_div_correct");
+        produced(1, current_.abi.fluid.vel, 3);
         check(sphk_dfsph_div_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0),
               "sphk_dfsph_div_error");
+        produced(2, bufferFloat.addr(), 1);
         ++iter;
-        if (errorThreshold >= 0.0f) check(sphk_reduce_abs_sum(ctx, error.addr(), num, &totalError), "sphk_reduce_abs_sum");
+        if (errorThreshold >= 0.0f) totalError = reduceError(num);
     }
     return iter;
 }
@@ -243,11 +259,15 @@ int DFSPHSolver::project(std::shared_ptr<SPHParticles>& fluids, const std::share
     auto iter = 0;
     // warm stiffness of the previous step follows its particle (:170-171)
     check(sphk_permute(ctx, denWarmStiff.addr(), 1, num), "sphk_permute");
+    // (ghost particles carry their warm stiffness with them: it travels with the candidates and is permuted with the rest)
     check(sphk_dfsph_den_correct(ctx, &current_.abi, denWarmStiff.addr(), dt), "sphk_dfsph_den_correct");
+    produced(1, current_.abi.fluid.vel, 3);
     check(sphk_dfsph_den_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0, nullptr),
           "sphk_dfsph_den_error");
+    produced(2, bufferFloat.addr(), 1);
     check(sphk_copy(ctx, denWarmStiff.addr(), bufferFloat.addr(), num), "sphk_copy");     // :185
-    if (errorThreshold >= 0.0f && deviceLoops_) {
+    const float thresholdCount = static_cast<float>(globalCount_ >= 0 ? globalCount_ : num);
+    if (errorThreshold >= 0.0f && deviceLoops_ && !fieldHook_) {
         check(sphk_loop_begin(ctx, 1, 2, maxIter_, errorThreshold * num * rho0, 2), "sphk_loop_begin");
         for (int k = 0; k < maxIter_; ++k) {
             check(sphk_dfsph_den_correct(ctx, &current_.abi, bufferFloat.addr(), dt), "sphk_dfsph_den_correct");
@@ -259,16 +279,30 @@ int DFSPHSolver::project(std::shared_ptr<SPHParticles>& fluids, const std::share
         check(sphk_loop_end(ctx, 1), "sphk_loop_end");
         return -1;
     }
-    while ((iter < 2 || totalError > errorThreshold * num * rho0) && iter < maxIter_) {
+    while ((iter < 2 || totalError > errorThreshold * thresholdCount * rho0) && iter < maxIter_) {
         check(sphk_dfsph_den_correct(ctx, &current_.abi, bufferFloat.addr(), dt), "sphk_dfsph_den_correct");
+        produced(1, current_.abi.fluid.vel, 3);
         check(sphk_dfsph_den_error(ctx, &current_.abi, alpha.addr(), error.addr(), bufferFloat.addr(), dt, rho0,
                                    denWarmStiff.addr()),
               "sphk_dfsph_den_error");                                                    // + :199-203 fused
+        produced(2, bufferFloat.addr(), 1);
         ++iter;
-        if (iter >= 2 && errorThreshold >= 0.0f)
-            check(sphk_reduce_abs_sum(ctx, error.addr(), num, &totalError), "sphk_reduce_abs_sum");
+        if (iter >= 2 && errorThreshold >= 0.0f) totalError = reduceError(num);
     }
     return iter;
+}
+
+// thrust::reduce(error, abs_plus), DFSPHSolver.cu:206,360 -- over the particles this rank owns, then over the ranks
+float DFSPHSolver::reduceError(int num) {
+    float local = 0.0f;
+    if (reduceHook_) {
+        int begin = 0, count = num;
+        if (ownedRange_) ownedRange_(begin, count);
+        check(sphk_reduce_abs_sum(current_.ctx, error.addr(begin), count, &local), "sphk_reduce_abs_sum");
+        return static_cast<float>(reduceHook_(static_cast<double>(local)));
+    }
+    check(sphk_reduce_abs_sum(current_.ctx, error.addr(), num, &local), "sphk_reduce_abs_sum");
+    return local;
 }
 
 int DFSPHSolver::loopIterations(int slot, int hostCount) const {
@@ -303,9 +337,12 @@ void PBDSolver::step(std::shared_ptr<SPHParticles>& fluids, const std::shared_pt
         // XSPH + colour gradient in one sweep (positions are final after the projection), then the surface sweep
         float* cg = colorGradBuffer();
         check(sphk_fused_pbd_xsph_color_grad(current_.ctx, &current_.abi, xSPH_c, rho0, cg, rhoB), "sphk_fused_pbd_xsph_color_grad");
+        producedVel(fluids); produced(0, cg, 3);
         check(sphk_surface(current_.ctx, &current_.abi, cg, dt, rho0, surfaceTensionIntensity, airPressure), "sphk_surface");
+        producedVel(fluids);
     } else {
         diffuse(fluids, cellStartFluid, cellSize, cellLength, rho0, radius, xSPH_c);
+        producedVel(fluids);
         if (surface)
             handleSurface(fluids, boundaries, cellStartFluid, cellStartBoundary, rho0, rhoB, cellSize, cellLength, radius,
                           dt, surfaceTensionIntensity, airPressure);
@@ -341,9 +378,11 @@ int PBDSolver::project(std::shared_ptr<SPHParticles>&, const std::shared_ptr<SPH
     while (iter < maxIter_) {
         check(sphk_pbd_density_lambda(current_.ctx, &current_.abi, bufferFloat.addr(), rho0, relaxation),
               "sphk_pbd_density_lambda");
+        produced(2, bufferFloat.addr(), 1);
         check(sphk_pbd_delta_pos_apply(current_.ctx, &current_.abi, bufferFloat.addr(),
                                        reinterpret_cast<float*>(bufferFloat3.addr()), rho0, sp),
               "sphk_pbd_delta_pos_apply");
+        produced(4, current_.abi.fluid.pos, 3);
         ++iter;
     }
     return iter;

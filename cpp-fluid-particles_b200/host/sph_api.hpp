@@ -8,7 +8,9 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <functional>
 #include <iostream>
 #include <memory>
 #include <type_traits>
@@ -51,7 +53,7 @@ inline void check(int rc, const char* what) {
 // BaseSolver::step) can reach it.
 class Engine {
 public:
-    Engine(int maxFluid, int maxBoundary, int3 cellSize, float cellLength);
+    Engine(int maxFluid, int maxBoundary, int3 cellSize, float cellLength, int3 origin = int3{0, 0, 0});
     ~Engine();
     Engine(const Engine&) = delete;
     Engine& operator=(const Engine&) = delete;
@@ -99,7 +101,10 @@ public:
     Particles& operator=(const Particles&) = delete;
     virtual ~Particles() noexcept {}
 
-    unsigned int size() const { return pos.length(); }
+    // (addition: a slab rank keeps capacity-sized arrays of which the first activeCount_ entries are live)
+    unsigned int size() const { return activeCount_ >= 0 ? static_cast<unsigned int>(activeCount_) : pos.length(); }
+    unsigned int capacity() const { return pos.length(); }
+    void setActiveCount(int n) { activeCount_ = n; }
     float3* getPosPtr() const { return pos.addr(); }
     float3* getVelPtr() const { return vel.addr(); }
     const DArray<float3>& getPos() const { return pos; }
@@ -113,6 +118,7 @@ protected:
     DArray<float3> pos;
     DArray<float3> vel;
     std::shared_ptr<sphb200::Engine> engine_;
+    int activeCount_ = -1;
 };
 
 // ---- SPHParticles.h:20-60 ---------------------------------------------------------------------
@@ -169,9 +175,20 @@ public:
     // addition: true when step() enqueues the same kernel sequence every call and never synchronises the host.
     // Only the three shipped solver types can say so: a user-derived solver (the reference API allows subclassing
     // BasicSPHSolver) has per-step host logic of its own, so it is never captured into a step graph.
-    virtual bool stepIsGraphSafe() const { return typeid(*this) == typeid(BasicSPHSolver); }
+    virtual bool stepIsGraphSafe() const { return typeid(*this) == typeid(BasicSPHSolver) && !fieldHook_; }
     // addition: bumped whenever a setting that changes the kernel sequence is modified (invalidates a captured graph)
     unsigned int configEpoch() const { return configEpoch_; }
+    // additions for the multi-GPU system (SlabSPHSystem): the solver classes stay what they are; after every sweep whose
+    // output a later sweep gathers from neighbours the solver tells the system, which refreshes that field on its ghost
+    // particles.  what: 1 = velocities, 2 = neighbour scalar (stiffness / lambda), 4 = positions, 0 = any other
+    // per-particle array (width 1 or 3 floats).  Unset on one GPU (no calls, no cost).
+    using FieldHook = std::function<void(int what, float* array, int width)>;
+    using ReduceHook = std::function<double(double)>;
+    void setFieldHook(FieldHook h) { fieldHook_ = std::move(h); ++configEpoch_; }
+    using RangeHook = std::function<void(int& begin, int& count)>;
+    void setReduceHook(ReduceHook h, long long globalCount, RangeHook owned) { reduceHook_ = std::move(h); globalCount_ = globalCount; ownedRange_ = std::move(owned); }
+    // the per-particle history array that must travel with a particle when it changes rank (nullptr: none)
+    virtual float* historyArray(int& width) { width = 0; return nullptr; }
     virtual ~BasicSPHSolver() noexcept {}
     virtual void step(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
                       const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
@@ -201,6 +218,12 @@ protected:
                            bool surface, bool colorGradReady);
     bool fusedSweeps_ = true;
     unsigned int configEpoch_ = 0;
+    FieldHook fieldHook_;
+    ReduceHook reduceHook_;
+    RangeHook ownedRange_;
+    long long globalCount_ = -1;
+    void produced(int what, float* array, int width) { if (fieldHook_) fieldHook_(what, array, width); }
+    void producedVel(const std::shared_ptr<SPHParticles>& f) { if (fieldHook_) fieldHook_(1, reinterpret_cast<float*>(f->getVelPtr()), 3); }
     float* colorGradBuffer() const { return reinterpret_cast<float*>(bufferColorGrad.addr()); }
     bool beginStep(std::shared_ptr<SPHParticles>& fluids, const std::shared_ptr<SPHParticles>& boundaries,
                    const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float radius,
@@ -225,7 +248,10 @@ public:
                       float visc, float3 G, float surfaceTensionIntensity, float airPressure) override;
     // fixed iteration counts (negative thresholds, Q11), or loop tests evaluated on the device: either way the step is a
     // fixed launch sequence without host synchronisation
-    bool stepIsGraphSafe() const override { return deviceLoops_ || (densityErrorThreshold < 0.0f && divergenceErrorThreshold < 0.0f); }
+    bool stepIsGraphSafe() const override {
+        return !fieldHook_ && (deviceLoops_ || (densityErrorThreshold < 0.0f && divergenceErrorThreshold < 0.0f));
+    }
+    float* historyArray(int& width) override { width = 1; return denWarmStiff.addr(); }
     // addition: false = the reference's host loop (one error sum read back per iteration, DFSPHSolver.cu:206,360)
     void setDeviceLoops(bool on) { if (on != deviceLoops_) ++configEpoch_; deviceLoops_ = on; }
     int lastDivergenceIterations() const { return loopIterations(0, itDiv_); }   // addition: iteration counts of the last step
@@ -237,6 +263,7 @@ protected:
                         int3 cellSize, float cellLength, float radius, float dt, float errorThreshold, int maxIter);
 private:
     int correctDivergenceError(float rho0, float dt, float errorThreshold, int maxIter, int num, bool firstErrorDone);
+    float reduceError(int num);
     DArray<float> alpha;
     DArray<float> bufferFloat;     // the stiffness kappa of the paper
     DArray<int> bufferInt;         // kept for layout parity; the re-sort it served is sphk_permute now
@@ -268,9 +295,10 @@ public:
                       const DArray<int>& cellStartFluid, const DArray<int>& cellStartBoundary, float3 spaceSize,
                       int3 cellSize, float cellLength, float radius, float dt, float rho0, float rhoB, float stiff,
                       float visc, float3 G, float surfaceTensionIntensity, float airPressure) override;
-    bool stepIsGraphSafe() const override { return posLastInitialized; }
+    bool stepIsGraphSafe() const override { return posLastInitialized && !fieldHook_; }
+    float* historyArray(int& width) override { width = 3; return reinterpret_cast<float*>(fluidPosLast.addr()); }
     void initializePosLast(const DArray<float3>& posFluid) {
-        CUDA_CALL(cudaMemcpy(fluidPosLast.addr(), posFluid.addr(), sizeof(float3) * fluidPosLast.length(),
+        CUDA_CALL(cudaMemcpy(fluidPosLast.addr(), posFluid.addr(), sizeof(float3) * std::min(fluidPosLast.length(), posFluid.length()),
                              cudaMemcpyDeviceToDevice));
         posLastInitialized = true;
     }

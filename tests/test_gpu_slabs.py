@@ -77,3 +77,38 @@ def test_slabs_match_single_gpu_nccl(built, solver, transport):
     out = _run(2, ["--backend", "nccl", "--solver", solver, "--steps", "3", "--jitter", "0.001"], timeout=100, env=env)
     assert out["ok"], out
     assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
+
+
+@pytest.mark.parametrize("solver", ["dfsph", "sph", "pbd"])
+def test_cpp_slab_system_matches_single_gpu(built, solver, tmp_path):
+    """The class-API system sharded over 2 GPUs (host/sph_slab.hpp: SlabSPHSystem, one process per GPU, file rendezvous,
+    native NCCL + peer-memory mailbox halos) against SPHSystem on one GPU, both through the reference's call sites
+    (app/sph_headless.cpp): the ranks' owned particles together must be the single-GPU particles, <= 1e-5 on position
+    and density (north_star).  Particles are matched by position (the ranks keep their own order)."""
+    import numpy as np
+    import torch
+    from scipy.spatial import cKDTree
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    cli = os.path.join(ROOT, "cpp-fluid-particles_b200", "sph_headless")
+    common = ["--solver", solver, "--frames", "6", "--quiet", "--block", "30", "40", "30"]
+    one = subprocess.run([cli] + common + ["--dump", str(tmp_path / "one")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=120)
+    assert one.returncode == 0, one.stdout[-2000:]
+    two = subprocess.run([cli] + common + ["--ranks", "2", "--dump", str(tmp_path / "two")], stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, timeout=180)
+    assert two.returncode == 0, two.stdout[-2000:]
+    lines = [json.loads(l) for l in two.stdout.splitlines() if l.startswith("{")]
+    assert sorted(l["rank"] for l in lines) == [0, 1], two.stdout[-2000:]
+    pos1 = np.fromfile(tmp_path / "one.pos.f32", dtype=np.float32).reshape(-1, 3)
+    den1 = np.fromfile(tmp_path / "one.density.f32", dtype=np.float32)
+    pos2 = np.concatenate([np.fromfile(tmp_path / f"two.rank{r}.pos.f32", dtype=np.float32).reshape(-1, 3) for r in range(2)])
+    den2 = np.concatenate([np.fromfile(tmp_path / f"two.rank{r}.density.f32", dtype=np.float32) for r in range(2)])
+    assert pos2.shape == pos1.shape and sum(l["n_owned"] for l in lines) == pos1.shape[0], (pos1.shape, pos2.shape, lines)
+    assert min(l["n_owned"] for l in lines) > 0.3 * pos1.shape[0], lines
+    d, idx = cKDTree(pos2).query(pos1)
+    assert np.unique(idx).size == idx.size, "the match between the two runs is not one-to-one"
+    scale = max(1.0, float(np.abs(pos1).max()))
+    assert float(d.max()) <= 1e-5 * scale, float(d.max())
+    rel = np.abs(den2[idx] - den1) / np.maximum(np.abs(den1), 1e-12)
+    assert float(rel.max()) <= 1e-5, float(rel.max())
