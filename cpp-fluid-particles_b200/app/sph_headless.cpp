@@ -8,7 +8,7 @@
 // (positions, densities and the generate_dots colours of vbo.cu:26-51) for offline viewing.
 //
 //   sph_headless [--solver sph|dfsph|pbd] [--frames N] [--box L | --box LX LY LZ] [--block NX NY NZ] [--origin X Y Z]
-//                [--dt DT] [--iters K] [--dump PREFIX] [--quiet] [--emit-scene PREFIX] [--ranks N [--rank R --rendezvous DIR]]
+//                [--dt DT] [--iters K] [--dump PREFIX] [--quiet] [--emit-scene PREFIX] [--ranks N [--rank R --rendezvous DIR]] [--bullets K]
 // --emit-scene writes the generated scene (PREFIX.fluid.f32, PREFIX.boundary.f32) and exits: needs no GPU, lets a
 // test compare this generator with the python one the benchmarks use.
 // --ranks N runs the same scene on N GPUs through SlabSPHSystem (host/sph_slab.hpp: the class API sharded by x-slabs):
@@ -52,6 +52,7 @@ struct Options {
     int iters = 0;                            // > 0: fixed iteration count (DFSPH thresholds -1, Q11)
     std::string dump, emitScene;
     bool quiet = false;
+    int bullets = 0;                          // test aid: this many top-layer particles start at ~3 cell planes per step
     int ranks = 1, rank = -1;                 // --ranks N: SlabSPHSystem on N GPUs; --rank R: this process is rank R
     std::string rendezvous;
 };
@@ -67,6 +68,7 @@ bool parse(int argc, char** argv, Options& o) {
         else if (a == "--dump" && need(i, 1)) o.dump = argv[++i];
         else if (a == "--emit-scene" && need(i, 1)) o.emitScene = argv[++i];
         else if (a == "--quiet") o.quiet = true;
+        else if (a == "--bullets" && need(i, 1)) o.bullets = std::atoi(argv[++i]);
         else if (a == "--ranks" && need(i, 1)) o.ranks = std::atoi(argv[++i]);
         else if (a == "--rank" && need(i, 1)) o.rank = std::atoi(argv[++i]);
         else if (a == "--rendezvous" && need(i, 1)) o.rendezvous = argv[++i];
@@ -133,6 +135,37 @@ bool write_floats(const std::string& path, const std::vector<float>& v) {
     const bool ok = std::fwrite(v.data(), sizeof(float), v.size(), f) == v.size();
     std::fclose(f);
     return ok;
+}
+
+// --bullets: the chosen top-layer lattice particles (found by position among slots [begin, begin + count): the lattice
+// survives the constructor's step 0) get a velocity of about three cell planes per step, alternately +x / -x, and upwards.
+// What a violent impact does to a few particles; on several GPUs it exercises the stray routing of SlabSPHSystem.
+int shoot(const Options& o, float spacing, float dt, const std::shared_ptr<SPHParticles>& fluids, size_t begin, size_t count) {
+    if (o.bullets <= 0 || count == 0) return 0;
+    std::vector<float3> pos(count), vel(count);
+    if (cudaMemcpy(pos.data(), fluids->getPosPtr() + begin, count * sizeof(float3), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(vel.data(), fluids->getVelPtr() + begin, count * sizeof(float3), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    const float speed = 30.0f * 0.004f / dt;
+    int hit = 0;
+    for (size_t i = 0; i < count; ++i) {
+        const int ix = static_cast<int>(std::lround((pos[i].x - o.origin[0]) / spacing)), iy = static_cast<int>(std::lround((pos[i].y - o.origin[1]) / spacing)),
+                  iz = static_cast<int>(std::lround((pos[i].z - o.origin[2]) / spacing));
+        if (iy != o.block[1] - 1) continue;
+        for (int b = 0; b < o.bullets; ++b)
+            if (ix == static_cast<int>((b + 0.5) * o.block[0] / o.bullets) && iz == o.block[2] / 2 + (b % 3) - 1) {
+                const float3 v = make_float3(b % 2 == 0 ? speed : -speed, 0.7f * speed, 0.0f);
+                if (o.solver == "pbd")      // PBD derives the velocity from the positions (PBDSolver.cu:56): displace the particle instead
+                    pos[i] = make_float3(pos[i].x + dt * v.x, pos[i].y + dt * v.y, pos[i].z + dt * v.z);
+                else
+                    vel[i] = v;
+                ++hit;
+            }
+    }
+    if (hit && (cudaMemcpy(fluids->getVelPtr() + begin, vel.data(), count * sizeof(float3), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(fluids->getPosPtr() + begin, pos.data(), count * sizeof(float3), cudaMemcpyHostToDevice) != cudaSuccess))
+        return -1;
+    return hit;
 }
 
 }  // namespace
@@ -240,12 +273,19 @@ int main(int argc, char** argv) {
         return 4;
     }
 
+    if (o.bullets > 0) {
+        const int hit = slab ? shoot(o, sphSpacing, dt, pSlab->getFluids(), static_cast<size_t>(pSlab->ownedBegin()), static_cast<size_t>(pSlab->size()))
+                             : shoot(o, sphSpacing, dt, pSystem->getFluids(), 0, pSystem->getFluids()->size());
+        if (hit < 0 || (!slab && hit != o.bullets)) { std::fprintf(stderr, "sph_headless: --bullets found %d of %d particles\n", hit, o.bullets); return 5; }
+    }
+
     // ---- oneStep(), main.cpp:300-306 ----
-    int frameId = 0;
+    int frameId = 0, straysRouted = 0;
     float totalTime = 0.0f, worst = 0.0f;
     for (; frameId < o.frames;) {
         ++frameId;
         const auto milliseconds = slab ? pSlab->step() : pSystem->step();
+        if (slab && o.bullets > 0) straysRouted += pSlab->straysRouted();
         totalTime += milliseconds;
         worst = milliseconds > worst ? milliseconds : worst;
         if (!o.quiet)
@@ -283,9 +323,9 @@ int main(int argc, char** argv) {
     }
     const float avg = frameId ? totalTime / float(frameId) : 0.0f;
     if (slab) {
-        std::printf("{\"solver\": \"%s\", \"rank\": %d, \"ranks\": %d, \"n_fluid\": %d, \"n_owned\": %d, \"halo\": \"%s\", \"dt\": %g, "
+        std::printf("{\"solver\": \"%s\", \"rank\": %d, \"ranks\": %d, \"n_fluid\": %d, \"n_owned\": %d, \"halo\": \"%s\", \"strays_routed\": %d, \"dt\": %g, "
                     "\"frames\": %d, \"avg_ms_per_frame\": %.4f, \"max_ms_per_frame\": %.4f}\n",
-                    o.solver.c_str(), o.rank, o.ranks, nFluid, pSlab->size(), pSlab->haloTransport(), dt, frameId, avg, worst);
+                    o.solver.c_str(), o.rank, o.ranks, nFluid, pSlab->size(), pSlab->haloTransport(), straysRouted, dt, frameId, avg, worst);
         std::fflush(stdout);
         return 0;
     }

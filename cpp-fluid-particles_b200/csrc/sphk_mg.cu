@@ -44,6 +44,7 @@ struct NcclApi {
     int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool ok = false;
 };
@@ -66,6 +67,7 @@ NcclApi load_nccl() {
     api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
     api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
     api.ok = all;
     return api;
@@ -647,6 +649,138 @@ extern "C" int sphk_mg_check(sphk_mg_comm* m, int* error_bits_host) {
     SPHK_CUDA_TRY(cudaMemcpyAsync(&e, &tail->error, sizeof(e), cudaMemcpyDeviceToHost, m->stream));
     SPHK_CUDA_TRY(cudaStreamSynchronize(m->stream));
     *error_bits_host = static_cast<int>(e);
+    return SPHK_OK;
+}
+
+// ---- strays: owned particles that crossed two or more cell planes in x since the last search ----------------------------------
+// The candidate exchange covers particles that move at most ONE plane per step (two candidate planes per side).  A violent
+// impact produces a few hundred particles that do not (the reference's own DFSPH setting of BASELINE.json: 4 + 4 fixed
+// iterations, dt = 0.004, shoots particles across tens of planes once the block hits the floor, around step 40 of the dam
+// break).  They are taken out of the regular flow and routed to everybody instead:
+//   collect : every owned particle compares the plane its sorted slot belongs to (binary search in the plane offsets of the
+//             cell ranges) with the plane of its position now (the search's own hash); |difference| >= 2 -> its row of the carried
+//             arrays goes into this rank's block and its position leaves the world, so whoever holds a copy of it (its owner,
+//             a neighbour that receives it as a candidate) drops it at the next search
+//   gather  : the fixed-size blocks of all ranks, one all-gather
+//   append  : world * capacity slots behind the assembled set [left candidates | own | right candidates]: the strays of rank
+//             0, 1, ... in block order -- the same sequence on every rank, so the ordering contract of the halos holds for
+//             them as well -- unused slots out of the world.  The search keeps a stray on the rank(s) whose window it landed in.
+namespace {
+constexpr int kStrayHeader = 4;                 // floats: {int count, 3 x pad}
+constexpr float kOutOfWorld = -1.0e6f;
+struct StrayArrays { float* a[4]; int w[4]; int off[4]; int k; int stride; };
+
+bool stray_arrays(StrayArrays& A, int narrays, float* const* arrays, const int* widths) {
+    if (narrays < 1 || narrays > 4 || !arrays || !widths || widths[0] != 3) return false;
+    A.k = narrays; A.stride = 0;
+    for (int i = 0; i < narrays; ++i) {
+        if (!arrays[i] || widths[i] < 1 || widths[i] > 3) return false;
+        A.a[i] = arrays[i]; A.w[i] = widths[i]; A.off[i] = A.stride; A.stride += widths[i];
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_strays_collect(const int* __restrict__ cs, int planeCells, int nPlanes, int begin, int count, float cellLength, int orgX,
+                 StrayArrays A, float* __restrict__ block, int capacity) {
+    const int t = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (t >= count) return;
+    const int i = begin + t;
+    const int pNow = cell_coord(A.a[0][3 * static_cast<size_t>(i)], cellLength) - orgX;
+    int lo = 0, hi = nPlanes;                   // the plane slot i was sorted into: largest p with cs[p * planeCells] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(cs + static_cast<size_t>(mid) * planeCells) <= i) lo = mid; else hi = mid;
+    }
+    const int d = pNow - lo;
+    if (d > -2 && d < 2) return;
+    const int slot = atomicAdd(reinterpret_cast<int*>(block), 1);
+    if (slot >= capacity) return;               // stays in place; count > capacity is reported by the append
+    float* row = block + kStrayHeader + static_cast<size_t>(slot) * A.stride;
+    for (int a = 0; a < A.k; ++a)
+        for (int c = 0; c < A.w[a]; ++c) row[A.off[a] + c] = A.a[a][static_cast<size_t>(A.w[a]) * i + c];
+    A.a[0][3 * static_cast<size_t>(i)] = kOutOfWorld; A.a[0][3 * static_cast<size_t>(i) + 1] = kOutOfWorld;
+    A.a[0][3 * static_cast<size_t>(i) + 2] = kOutOfWorld;
+}
+
+__global__ void __launch_bounds__(SPHK_BLOCK)
+k_strays_append(const float* __restrict__ gathered, int world, int capacity, StrayArrays A, int dstBegin, unsigned int* errorWord) {
+    const int t = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (t >= world * capacity) return;
+    const int r = t / capacity, j = t - r * capacity;
+    const float* block = gathered + static_cast<size_t>(r) * (kStrayHeader + static_cast<size_t>(capacity) * A.stride);
+    const int cnt = *reinterpret_cast<const int*>(block);
+    const size_t dst = static_cast<size_t>(dstBegin) + t;
+    if (j < cnt) {
+        const float* row = block + kStrayHeader + static_cast<size_t>(j) * A.stride;
+        for (int a = 0; a < A.k; ++a)
+            for (int c = 0; c < A.w[a]; ++c) A.a[a][A.w[a] * dst + c] = row[A.off[a] + c];
+    } else {
+        for (int a = 0; a < A.k; ++a)
+            for (int c = 0; c < A.w[a]; ++c) A.a[a][A.w[a] * dst + c] = a == 0 ? kOutOfWorld : 0.0f;
+    }
+    if (j == 0 && cnt > capacity && errorWord) atomicOr(errorWord, 16u);
+}
+}  // namespace
+
+extern "C" long long sphk_strays_block_floats(int capacity, int narrays, const int* widths) {
+    if (capacity < 0 || narrays < 1 || narrays > 4 || !widths) return -1;
+    long long stride = 0;
+    for (int i = 0; i < narrays; ++i) stride += widths[i];
+    return kStrayHeader + static_cast<long long>(capacity) * stride;
+}
+
+extern "C" int sphk_strays_collect(sphk_ctx* c, const int* cell_start_fluid, int own_begin, int own_count, int narrays,
+                                   float* const* arrays, const int* widths, float* block, int capacity) {
+    StrayArrays A;
+    if (!c || !cell_start_fluid || !block || capacity < 1 || own_begin < 0 || own_count < 0 || !stray_arrays(A, narrays, arrays, widths))
+        return SPHK_ERR_INVALID;
+    SPHK_CUDA_TRY(cudaMemsetAsync(block, 0, kStrayHeader * sizeof(float), c->stream));
+    if (own_count > 0) {
+        k_strays_collect<<<sphk_blocks(own_count), SPHK_BLOCK, 0, c->stream>>>(cell_start_fluid, c->cs.y * c->cs.z, c->cs.x, own_begin,
+                                                                              own_count, c->cellLength, c->org.x, A, block, capacity);
+        c->launches++;
+    }
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+static int strays_append(sphk_ctx* c, const float* gathered, int world, int capacity, int narrays, float* const* arrays,
+                         const int* widths, int dst_begin, unsigned int* errorWord) {
+    StrayArrays A;
+    if (!c || !gathered || world < 1 || capacity < 1 || dst_begin < 0 || !stray_arrays(A, narrays, arrays, widths)) return SPHK_ERR_INVALID;
+    k_strays_append<<<sphk_blocks(world * capacity), SPHK_BLOCK, 0, c->stream>>>(gathered, world, capacity, A, dst_begin, errorWord);
+    c->launches++;
+    SPHK_CUDA_TRY(cudaGetLastError());
+    return SPHK_OK;
+}
+
+extern "C" int sphk_strays_append(sphk_ctx* c, const float* gathered, int world, int capacity, int narrays, float* const* arrays,
+                                  const int* widths, int dst_begin) {
+    return strays_append(c, gathered, world, capacity, narrays, arrays, widths, dst_begin, nullptr);
+}
+
+/* all-gather of this rank's block + append (overflow raises bit 4 of the error word read by sphk_mg_check) */
+extern "C" int sphk_mg_strays_route(sphk_mg_comm* m, sphk_ctx* c, const float* block, float* gathered, int capacity, int narrays,
+                                    float* const* arrays, const int* widths, int dst_begin) {
+    if (!m || !c || !block || !gathered || m->stream != c->stream) return SPHK_ERR_INVALID;
+    const long long floats = sphk_strays_block_floats(capacity, narrays, widths);
+    if (floats < 0) return SPHK_ERR_INVALID;
+    SPHK_NCCL_TRY(nccl().AllGather(block, gathered, static_cast<size_t>(floats), kNcclFloat32, m->comm, m->stream));
+    m->bytesSent += floats * 4; m->messages++;
+    unsigned int* err = nullptr;
+    if (m->mail) err = &reinterpret_cast<MailTail*>(m->mail + flags_offset(m))->error;
+    return strays_append(c, gathered, m->world, capacity, narrays, arrays, widths, dst_begin, err);
+}
+
+/* {count of rank 0, count of rank 1, ...} of an all-gathered set of blocks (synchronises the stream): introspection / tests */
+extern "C" int sphk_strays_counts(sphk_ctx* c, const float* gathered, int world, int capacity, int narrays, const int* widths, int* counts_host) {
+    if (!c || !gathered || !counts_host || world < 1) return SPHK_ERR_INVALID;
+    const long long floats = sphk_strays_block_floats(capacity, narrays, widths);
+    if (floats < 0) return SPHK_ERR_INVALID;
+    SPHK_CUDA_TRY(cudaMemcpy2DAsync(counts_host, sizeof(int), gathered, static_cast<size_t>(floats) * sizeof(float), sizeof(int),
+                                    static_cast<size_t>(world), cudaMemcpyDeviceToHost, c->stream));
+    SPHK_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SPHK_OK;
 }
 

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <thread>
@@ -119,8 +120,12 @@ SlabSPHSystem::SlabSPHSystem(std::shared_ptr<SPHParticles>& fluidParticles, std:
     for (size_t i = 0; i < hpos.size(); ++i)
         if (plane[i] >= x0_ && plane[i] < x1_) mine.push_back(hpos[i]);
     const int nMine = static_cast<int>(mine.size());
+    if (boot_.world > 1) {
+        const char* e = std::getenv("SPHK_SLAB_STRAYS");
+        strayCap_ = e ? std::max(std::atoi(e), 0) : 1024;
+    }
     // (never above the global count: the solver's own buffers were sized with it at the reference call site, main.cpp:119-130)
-    cap_ = std::min(static_cast<int>(std::max<double>(nMine, static_cast<double>(nGlobal_) / boot_.world) * 1.6) + 4096, nGlobal_);
+    cap_ = std::min(static_cast<int>(std::max<double>(nMine, static_cast<double>(nGlobal_) / boot_.world) * 1.6) + 4096 + boot_.world * strayCap_, nGlobal_);
     mine.resize(static_cast<size_t>(cap_), make_float3(0.f, 0.f, 0.f));
     fluids_ = std::make_shared<SPHParticles>(mine);
     hpos.clear(); hpos.shrink_to_fit(); plane.clear(); plane.shrink_to_fit();
@@ -191,6 +196,8 @@ SlabSPHSystem::~SlabSPHSystem() noexcept {
     if (engine_ && engine_->ok()) sphk_synchronize(engine_->ctx());
     if (comm_) sphk_mg_destroy(comm_);
     if (dBounds_) cudaFree(dBounds_);
+    if (strayBlock_) cudaFree(strayBlock_);
+    if (strayGathered_) cudaFree(strayGathered_);
     if (evStart_) cudaEventDestroy(evStart_);
     if (evStop_) cudaEventDestroy(evStop_);
 }
@@ -267,6 +274,37 @@ void SlabSPHSystem::halo(int what, float* array, int width) {
     check(sphk_mg_halo(comm_, engine_->ctx(), &s, what, array, width, haloRanges_), "sphk_mg_halo");
 }
 
+// slabs.SlabSystem._collect_strays: owned particles that crossed two or more planes since the last search leave the regular flow
+void SlabSPHSystem::collectStrays() {
+    auto* known = dynamic_cast<BasicSPHSolver*>(solver_.get());
+    int histWidth = 0;
+    float* hist = known->historyArray(histWidth);
+    float* live[3] = {reinterpret_cast<float*>(fluids_->getPosPtr()), reinterpret_cast<float*>(fluids_->getVelPtr()), hist};
+    const int widths[3] = {3, 3, histWidth};
+    const int k = hist ? 3 : 2;
+    if (!strayBlock_) {
+        const long long nf = sphk_strays_block_floats(strayCap_, k, widths);
+        CUDA_CALL(cudaMalloc(reinterpret_cast<void**>(&strayBlock_), sizeof(float) * static_cast<size_t>(nf)));
+        CUDA_CALL(cudaMalloc(reinterpret_cast<void**>(&strayGathered_), sizeof(float) * static_cast<size_t>(nf) * boot_.world));
+    }
+    check(sphk_strays_collect(engine_->ctx(), csF_->addr(), r_.own[0], r_.own[1] - r_.own[0], k, live, widths, strayBlock_, strayCap_),
+          "sphk_strays_collect");
+    strayPending_ = true;
+}
+
+int SlabSPHSystem::straysRouted() {
+    if (!strayGathered_) return 0;
+    auto* known = dynamic_cast<BasicSPHSolver*>(solver_.get());
+    int histWidth = 0;
+    const int k = known->historyArray(histWidth) ? 3 : 2;
+    const int widths[3] = {3, 3, histWidth};
+    std::vector<int> counts(static_cast<size_t>(boot_.world), 0);
+    check(sphk_strays_counts(engine_->ctx(), strayGathered_, boot_.world, strayCap_, k, widths, counts.data()), "sphk_strays_counts");
+    int total = 0;
+    for (const int c : counts) total += c;
+    return total;
+}
+
 // slabs.SlabSystem._begin_step_native: candidates -> assembled set -> one search -> ranges, counts agreed for the next step
 void SlabSPHSystem::beginStep() {
     sphk_ctx* ctx = engine_->ctx();
@@ -293,8 +331,8 @@ void SlabSPHSystem::beginStep() {
     }
     const int nl = L ? candFrom_[0] : 0, nr = R ? candFrom_[1] : 0;
     const int own0 = r_.own[0], nOwnPrev = r_.own[1] - r_.own[0];
-    const int nAll = nl + nOwnPrev + nr;
-    if (nAll > cap_) { printf("SlabSPHSystem: rank %d: capacity %d exceeded by %d local particles\n", boot_.rank, cap_, nAll); return; }
+    int nAll = nl + nOwnPrev + nr;
+    if (nAll + (strayPending_ ? boot_.world * strayCap_ : 0) > cap_) { printf("SlabSPHSystem: rank %d: capacity %d exceeded by %d local particles\n", boot_.rank, cap_, nAll); return; }
     // carried arrays: pos, vel (+ the solver's history array), received straight into their slots of the assembled set
     float* live[3] = {reinterpret_cast<float*>(fluids_->getPosPtr()), reinterpret_cast<float*>(fluids_->getVelPtr()), hist};
     float* alt[3] = {reinterpret_cast<float*>(altPos_->addr()), reinterpret_cast<float*>(altVel_->addr()), altHist_->addr()};
@@ -308,8 +346,14 @@ void SlabSPHSystem::beginStep() {
     for (int a = 0; a < k; ++a) {
         const size_t wd = static_cast<size_t>(widths[a]);
         check(sphk_copy(ctx, alt[a] + wd * nl, live[a] + wd * own0, static_cast<int>(wd) * nOwnPrev), "sphk_copy");
-        check(sphk_copy(ctx, live[a], alt[a], static_cast<int>(wd) * nAll), "sphk_copy");     // (DArray pointers are fixed: copy back)
     }
+    if (strayPending_ && comm_) {                   // the strays of every rank, behind the candidates (same order everywhere)
+        check(sphk_mg_strays_route(comm_, ctx, strayBlock_, strayGathered_, strayCap_, k, alt, widths, nAll), "sphk_mg_strays_route");
+        nAll += boot_.world * strayCap_;
+    }
+    strayPending_ = false;
+    for (int a = 0; a < k; ++a)                      // (DArray pointers are fixed: copy back)
+        check(sphk_copy(ctx, live[a], alt[a], widths[a] * nAll), "sphk_copy");
     searchAll(nAll);
     int b[8];
     readBounds(b);
@@ -342,6 +386,7 @@ float SlabSPHSystem::step() {
     if (!ok_) return 0.0f;
     cudaStream_t st = engine_->stream();
     CUDA_CALL(cudaEventRecord(evStart_, st));
+    if (strayCap_ > 0 && haveRanges_ && comm_) collectStrays();
     beginStep();
     try {
         solver_->step(fluids_, boundaries_, *csF_, *csB_, spaceSize_, localCellSize_, cellLength_, radius_, dt_, rho0_, rhoB_, stiff_,

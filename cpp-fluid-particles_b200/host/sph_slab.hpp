@@ -47,6 +47,7 @@ public:
     // the LOCAL set [ghost-left | owned | ghost-right] (sorted by local cell index) and the local boundary set
     auto getFluids() const { return static_cast<const std::shared_ptr<SPHParticles>>(fluids_); }
     auto getBoundaries() const { return static_cast<const std::shared_ptr<SPHParticles>>(boundaries_); }
+    int straysRouted();                                 // strays all ranks collected for the last step (synchronises; introspection)
     const char* haloTransport() const { return transport_ == 1 ? "peer-memory mailboxes" : "NCCL send/recv"; }
 
 private:
@@ -70,6 +71,11 @@ private:
     std::unique_ptr<DArray<float3>> altPos_, altVel_;
     std::unique_ptr<DArray<float>> altHist_;
     int* dBounds_ = nullptr;          // device: the 8 plane offsets gathered from csF_
+    // strays (include/sphk.h): particles that crossed two or more planes in a step are routed to every rank
+    int strayCap_ = 0;                // per rank and step; SPHK_SLAB_STRAYS (default 1024, 0 = off)
+    float *strayBlock_ = nullptr, *strayGathered_ = nullptr;
+    bool strayPending_ = false;
+    void collectStrays();
     int x0_ = 0, x1_ = 0, w_ = 0, planeCells_ = 0, cap_ = 0, nGlobal_ = 0;
     int nOwn_ = 0, ownBegin_ = 0, nGhostL_ = 0, nGhostR_ = 0;
     bool haveRanges_ = false;

@@ -143,6 +143,14 @@ class SlabExchange:
                 recvs.append((from_right, self.right))
         self._p2p(sends, recvs)
 
+    def all_gather(self, block: torch.Tensor) -> torch.Tensor:
+        """Every rank's `block` (same size everywhere), concatenated in rank order."""
+        send = block.detach().cpu().contiguous() if self.stage else block.contiguous()
+        parts = [torch.empty_like(send) for _ in range(self.world)]
+        dist.all_gather(parts, send, group=self.group)
+        self.bytes_sent += send.numel() * send.element_size(); self.messages += 1
+        return torch.cat(parts).to(block.device)
+
     def exchange_rows(self, to_left: torch.Tensor, to_right: torch.Tensor):
         """Variable-size row exchange: counts first, then the rows.  Returns (rows_from_left, rows_from_right)."""
         nl, nr = self.exchange_counts(to_left.shape[0] if self.left is not None else 0,
@@ -152,6 +160,58 @@ class SlabExchange:
         fr = torch.empty((nr, width), dtype=to_left.dtype, device=self.device)
         self.exchange(to_left.contiguous(), to_right.contiguous(), fl, fr)
         return fl, fr
+
+
+# ---- strays: owned particles that crossed two or more planes since the last sort (include/sphk.h, "Strays") ----------------
+# The candidate exchange below covers one plane of motion per step.  The reference's own DFSPH benchmark setting (4 + 4 fixed
+# iterations, dt = 0.004) shoots a few hundred particles across tens of planes once the block hits the floor (around step 40
+# of the dam break: tools/plane_skip_probe.py), so such particles are taken out of the regular flow and sent to EVERY rank:
+# collect (rows into a fixed-size block, position out of the world) -> all-gather -> append behind the assembled set, the
+# same sequence on every rank.  The next sort keeps a stray where it landed and drops it everywhere else.
+STRAY_HEADER = 4                  # floats in front of the rows: {int32 count, 3 x pad}
+OUT_OF_WORLD = -1.0e6
+
+
+def stray_block_floats(capacity: int, widths) -> int:
+    return STRAY_HEADER + capacity * int(sum(widths))
+
+
+def _widths(arrays):
+    return [1 if a.dim() == 1 else int(a.shape[1]) for a in arrays]
+
+
+def collect_strays_host(arrays, own: tuple, plane_sorted, plane_now, capacity: int) -> torch.Tensor:
+    """torch statement of sphk_strays_collect (what the kernel does; the CPU tests run on it): plane_sorted / plane_now are
+    the x-plane a slot of the owned range was sorted into and the plane of its position now.  Returns the block."""
+    widths = _widths(arrays)
+    stride = sum(widths)
+    block = torch.zeros(stray_block_floats(capacity, widths), dtype=torch.float32, device=arrays[0].device)
+    idx = torch.nonzero((torch.as_tensor(plane_now) - torch.as_tensor(plane_sorted)).abs() >= 2).flatten() + own[0]
+    block[:1].view(torch.int32)[0] = int(idx.numel())
+    idx = idx[:capacity]
+    if idx.numel():
+        rows = torch.cat([a[idx].reshape(idx.numel(), w_) for a, w_ in zip(arrays, widths)], 1)
+        block[STRAY_HEADER:STRAY_HEADER + rows.numel()] = rows.flatten()
+        arrays[0][idx] = OUT_OF_WORLD
+    return block
+
+
+def append_strays_host(gathered: torch.Tensor, world: int, capacity: int, arrays, dst_begin: int) -> int:
+    """torch statement of sphk_strays_append: world * capacity slots from dst_begin on.  Returns that slot count."""
+    widths = _widths(arrays)
+    stride = sum(widths)
+    blocks = gathered.reshape(world, stray_block_floats(capacity, widths))
+    counts = blocks[:, :1].contiguous().view(torch.int32).flatten().clamp(max=capacity)
+    rows = blocks[:, STRAY_HEADER:].reshape(world, capacity, stride).clone()
+    unused = torch.arange(capacity, device=gathered.device)[None, :] >= counts[:, None]
+    rows[unused] = 0.0
+    rows[..., :3][unused] = OUT_OF_WORLD
+    rows = rows.reshape(world * capacity, stride)
+    c = 0
+    for a, w_ in zip(arrays, widths):
+        a[dst_begin:dst_begin + world * capacity] = rows[:, c:c + w_].reshape((world * capacity,) + tuple(a.shape[1:]))
+        c += w_
+    return world * capacity
 
 
 def exchange_candidates(ex: SlabExchange, arrays, alt, own: tuple, to_left: tuple, to_right: tuple) -> int:
@@ -214,6 +274,9 @@ def plane_ranges(b: tuple, w: int):
             "last": (sw if w >= 2 else s1, sw1), "ghost_l": (s0, s1), "ghost_r": (sw1, send)}
 
 
+_DIAG_NO_HALO = os.environ.get("SPHK_SLAB_DIAG_NOHALO", "0") == "1"
+
+
 class SlabSystem(SphkOps):
     """One rank of a slab-decomposed SPH system (DFSPH / WCSPH / PBD) over the libsphk C-ABI."""
 
@@ -236,6 +299,10 @@ class SlabSystem(SphkOps):
         # not needed here: a particle one plane off is simply migrated by the first step) --------------------
         device_scene = scene.fluid is None
         n_total = scene.n_fluid
+        # strays per rank and step that can be routed (SPHK_SLAB_STRAYS=0: off -- a particle that crosses two planes in a
+        # step then stops the run with the ghost-plane mismatch error); world * stray_cap slots are appended to every search
+        self.stray_cap = int(os.environ.get("SPHK_SLAB_STRAYS", "1024")) if world > 1 else 0
+        self._strays_pending = False
         self._n_scene_fluid = n_total
         if device_scene:
             # no host-side particle array.  The CDF comes from the nx lattice columns; the rank generates
@@ -249,7 +316,7 @@ class SlabSystem(SphkOps):
             cols = np.nonzero((col_plane >= x0) & (col_plane < x1))[0]
             j_begin, j_count = (int(cols[0]), int(cols.shape[0])) if cols.shape[0] else (0, 0)
             n_mine = ny * j_count * nz
-            cap = int(max(n_mine, n_total / world) * capacity_factor) + 4096
+            cap = int(max(n_mine, n_total / world) * capacity_factor) + 4096 + world * self.stray_cap
             fluid_dev = device_fluid_block(self.L, scene.lattice, self.device, self.stream, j_begin, j_count, capacity=cap)
             bpos, bmass = self._global_boundary_device(scene, x0, x1)
         else:
@@ -259,7 +326,7 @@ class SlabSystem(SphkOps):
             self.x0, self.x1, self.w = x0, x1, x1 - x0
             mine = scene.fluid[(plane >= x0) & (plane < x1)]
             n_mine = mine.shape[0]
-            cap = int(max(n_mine, n_total / world) * capacity_factor) + 4096
+            cap = int(max(n_mine, n_total / world) * capacity_factor) + 4096 + world * self.stray_cap
             # ---- boundary: masses from the GLOBAL boundary set (every rank computes them once), then the subset
             # in this rank's planes [x0-1, x1+1) ---------------------------------------------------------------
             bpos, bmass = self._global_boundary(scene)
@@ -446,6 +513,52 @@ class SlabSystem(SphkOps):
             arrs.append(self.pos_last)
         return arrs
 
+    def _array_args(self, arrays):
+        k = len(arrays)
+        return C.c_int(k), (C.c_void_p * k)(*[a.data_ptr() for a in arrays]), (C.c_int * k)(*_widths(arrays))
+
+    def _collect_strays(self):
+        """sphk_strays_collect over the owned range of the current sorted set (see "strays" at the top of the module)."""
+        self._refresh_ranges()
+        arrays = self._carried()
+        if not hasattr(self, "_stray_block"):
+            nf = stray_block_floats(self.stray_cap, _widths(arrays))
+            self._stray_block = torch.zeros(nf, dtype=torch.float32, device=self.device)
+            self._stray_gathered = torch.zeros(self.world * nf, dtype=torch.float32, device=self.device)
+        a, b = self._ranges["own"]
+        k, ptrs, widths = self._array_args(arrays)
+        check(self.L.sphk_strays_collect(self.ctx, _ptr(self.cs_fluid), C.c_int(a), C.c_int(b - a), k, ptrs, widths,
+                                         _ptr(self._stray_block), C.c_int(self.stray_cap)), "sphk_strays_collect")
+        self._strays_pending = True
+
+    def _route_strays(self, arrays, n_all: int) -> int:
+        """All-gather of the collected blocks + append at slot n_all of `arrays` (the set being assembled for the search).
+        Returns the new slot count."""
+        if not self._strays_pending:
+            return n_all
+        self._strays_pending = False
+        extra = self.world * self.stray_cap
+        if n_all + extra > self.cap:
+            raise RuntimeError(f"slab rank {self.rank}: capacity {self.cap} exceeded by {n_all} local particles + {extra} stray slots")
+        k, ptrs, widths = self._array_args(arrays)
+        if self.mg is not None:
+            check(self.L.sphk_mg_strays_route(self.mg, self.ctx, _ptr(self._stray_block), _ptr(self._stray_gathered), C.c_int(self.stray_cap),
+                                              k, ptrs, widths, C.c_int(n_all)), "sphk_mg_strays_route")
+        else:
+            self._stray_gathered.copy_(self.ex.all_gather(self._stray_block))
+            check(self.L.sphk_strays_append(self.ctx, _ptr(self._stray_gathered), C.c_int(self.world), C.c_int(self.stray_cap), k, ptrs, widths,
+                                            C.c_int(n_all)), "sphk_strays_append")
+        return n_all + extra
+
+    def stray_counts(self):
+        """Strays each rank collected in the last step that had any routing (synchronises; introspection)."""
+        if not hasattr(self, "_stray_gathered"):
+            return [0] * self.world
+        out = (C.c_int * self.world)()
+        k, _, widths = self._array_args(self._carried())
+        check(self.L.sphk_strays_counts(self.ctx, _ptr(self._stray_gathered), C.c_int(self.world), C.c_int(self.stray_cap), k, widths, out))
+        return list(out)
+
     def _search_all(self, n):
         """The C-ABI neighbour search over slots [0, n).  The history array (DFSPH warm stiffness, PBD last positions)
         is NOT permuted here: the solver sequence does that itself with the same permutation (DFSPHSolver.cu:170-171,
@@ -529,6 +642,7 @@ class SlabSystem(SphkOps):
             wd = 1 if a.dim() == 1 else a.shape[1]
             check(L.sphk_copy(self.ctx, C.c_void_p(d.data_ptr() + 4 * wd * nl), C.c_void_p(a.data_ptr() + 4 * wd * own0),
                               C.c_int(n_own * wd)), "sphk_copy")
+        n_all = self._route_strays(self._alt, n_all)
         self._swap_carried()
         self._search_all(n_all)
         b = self._bounds()
@@ -572,6 +686,8 @@ class SlabSystem(SphkOps):
         return ms / n
 
     def _halo(self, what: int, t: torch.Tensor):
+        if _DIAG_NO_HALO:                # timing diagnostic only (results are WRONG): what the halos cost a step
+            return
         if self._step_async:             # this step's ranges live on the device
             check(self.L.sphk_mg_halo_device(self.mg, self.ctx, self._s(), C.c_int(what), _ptr(t), C.c_int(1 if t.dim() == 1 else t.shape[1]),
                                              C.c_void_p(self._dev24.data_ptr() + 4 * 8), C.c_int(self.cap)), "sphk_mg_halo_device")
@@ -637,6 +753,7 @@ class SlabSystem(SphkOps):
             wd = 1 if a.dim() == 1 else a.shape[1]
             check(L.sphk_copy(self.ctx, C.c_void_p(d.data_ptr() + 4 * wd * nl), C.c_void_p(a.data_ptr() + 4 * wd * own0),
                               C.c_int(n_own * wd)), "sphk_copy")
+        n_all = self._route_strays(self._alt, n_all)
         self._swap_carried()
         self._search_all(n_all)
         d24 = self._dev24.data_ptr()
@@ -681,6 +798,7 @@ class SlabSystem(SphkOps):
             self._ranges = r
         r = self._ranges
         n_all = exchange_candidates(self.ex, arrays, self._alt, r["own"], r["to_left"], r["to_right"])
+        n_all = self._route_strays(arrays, n_all)
         self._search_all(n_all)
         b = self._bounds()
         self._ranges = r = plane_ranges(b, self.w)
@@ -853,6 +971,8 @@ class SlabSystem(SphkOps):
 
     def step(self):
         self._step_no += 1
+        if self.stray_cap and self._ranges is not None:
+            self._collect_strays()                      # (before a re-balance moves the window the sorted set refers to)
         if self.rebalance_every > 0 and self._step_no % self.rebalance_every == 0:
             self.rebalance()
         self.begin_step()

@@ -308,11 +308,33 @@ int  sphk_mg_halo_device(sphk_mg_comm* comm, sphk_ctx* ctx, const sphk_scene* s,
 int  sphk_mg_exchange_ints_async(sphk_mg_comm* comm, const int* device_to_left, const int* device_to_right, int count,
                                  int* pinned_from_left, int* pinned_from_right);
 int  sphk_mg_check_async(sphk_mg_comm* comm, int* pinned_error_bits);
-/* mailbox error word (0 = fine; bit 0/1 timed out waiting for left/right; bit 2/3 size mismatch from left/right).
+/* mailbox error word (0 = fine; bit 0/1 timed out waiting for left/right; bit 2/3 size mismatch from left/right; bit 4 more
+ * strays than the routing capacity, see sphk_mg_strays_route).
  * Synchronises the stream. */
 int  sphk_mg_check(sphk_mg_comm* comm, int* error_bits_host);
 /* {bytes sent, messages sent} by this rank so far */
 int  sphk_mg_stats(const sphk_mg_comm* comm, long long out_host[2]);
+/* Strays: owned particles that crossed TWO OR MORE cell planes in x since the last search (the candidate exchange covers
+ * one plane per step; the reference's own DFSPH benchmark setting shoots a few hundred particles across tens of planes
+ * once the block hits the floor).  They are routed to every rank instead.  `arrays` are the carried per-particle arrays
+ * (arrays[0] = positions, width 3; at most 4 arrays of width 1..3); a block is {int count, 3 pad, rows[capacity][sum of
+ * widths]} = sphk_strays_block_floats floats.
+ *   sphk_strays_collect: over the owned slots [own_begin, own_begin + own_count) of the set sorted by the last search
+ *     (cell_start_fluid are ITS cell ranges; call before sphk_set_grid moves the window): rows of the strays into `block`,
+ *     their positions out of the world (-1e6: dropped by the next search wherever a copy is held).
+ *   sphk_mg_strays_route: all-gathers the blocks (NCCL) into `gathered` (world blocks) and appends world * capacity slots
+ *     at dst_begin of `arrays` (the assembled set of the next search): the strays of rank 0, 1, ... -- the same order on
+ *     every rank -- unused slots out of the world.  count > capacity (the surplus stayed in place) raises bit 4 of the
+ *     error word of sphk_mg_check.  sphk_strays_append: the append alone, for blocks gathered through another channel.
+ *   sphk_strays_counts: the per-rank counts of a gathered set (synchronises; introspection). */
+long long sphk_strays_block_floats(int capacity, int narrays, const int* widths);
+int  sphk_strays_collect(sphk_ctx* ctx, const int* cell_start_fluid, int own_begin, int own_count, int narrays,
+                         float* const* arrays, const int* widths, float* block, int capacity);
+int  sphk_strays_append(sphk_ctx* ctx, const float* gathered, int world, int capacity, int narrays, float* const* arrays,
+                        const int* widths, int dst_begin);
+int  sphk_mg_strays_route(sphk_mg_comm* comm, sphk_ctx* ctx, const float* block, float* gathered, int capacity, int narrays,
+                          float* const* arrays, const int* widths, int dst_begin);
+int  sphk_strays_counts(sphk_ctx* ctx, const float* gathered, int world, int capacity, int narrays, const int* widths, int* counts_host);
 
 /* ---- introspection for parity tests --------------------------------------------------------- */
 /* copies the stable-sort permutation of the last fluid search (perm[s] = pre-sort index) to device

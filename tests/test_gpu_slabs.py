@@ -50,6 +50,21 @@ def test_slabs_rebalance_cuts(built, solver, world):
     assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
 
 
+@pytest.mark.parametrize("solver,world", [("dfsph", 3), ("pbd", 2), ("wcsph", 2)])
+def test_slabs_route_fast_particles(built, solver, world):
+    """Particles that cross several cell planes in ONE step (here: top-layer particles shot along +-x at ~3 planes per step;
+    in the benchmark scene: what the impact on the floor does around step 40) are outside the one-plane contract of the
+    candidate exchange.  They must be routed to their new owners and ghost planes (the "strays" of include/sphk.h) and the
+    result must stay the single-GPU result."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device")
+    out = _run(world, ["--backend", "gloo", "--same-gpu", "--solver", solver, "--steps", "5", "--bullets", "6"])
+    assert out["ok"], out
+    assert out["strays_routed"] >= 6, out
+    assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
+
+
 @pytest.mark.parametrize("solver", ["dfsph", "pbd"])
 def test_slabs_device_side_scene(built, solver):
     """every rank generates its own lattice columns and the boundary shell on the device (no host-side
@@ -79,8 +94,20 @@ def test_slabs_match_single_gpu_nccl(built, solver, transport):
     assert sum(c[1] for c in out["counts"]) == out["steps"][0]["n"]
 
 
-@pytest.mark.parametrize("solver", ["dfsph", "sph", "pbd"])
-def test_cpp_slab_system_matches_single_gpu(built, solver, tmp_path):
+@pytest.mark.parametrize("solver", ["dfsph", "pbd"])
+def test_slabs_route_fast_particles_native(built, solver):
+    """test_slabs_route_fast_particles over the native transports on 2 GPUs (NCCL all-gather of the stray blocks, host-free
+    step assembly)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    out = _run(2, ["--backend", "nccl", "--solver", solver, "--steps", "5", "--bullets", "6"], timeout=100)
+    assert out["ok"], out
+    assert out["strays_routed"] >= 6, out
+
+
+@pytest.mark.parametrize("solver,bullets", [("dfsph", 0), ("sph", 0), ("pbd", 0), ("dfsph", 6), ("pbd", 6)])
+def test_cpp_slab_system_matches_single_gpu(built, solver, bullets, tmp_path):
     """The class-API system sharded over 2 GPUs (host/sph_slab.hpp: SlabSPHSystem, one process per GPU, file rendezvous,
     native NCCL + peer-memory mailbox halos) against SPHSystem on one GPU, both through the reference's call sites
     (app/sph_headless.cpp): the ranks' owned particles together must be the single-GPU particles, <= 1e-5 on position
@@ -91,7 +118,7 @@ def test_cpp_slab_system_matches_single_gpu(built, solver, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     cli = os.path.join(ROOT, "cpp-fluid-particles_b200", "sph_headless")
-    common = ["--solver", solver, "--frames", "6", "--quiet", "--block", "30", "40", "30"]
+    common = ["--solver", solver, "--frames", "6", "--quiet", "--block", "30", "40", "30", "--bullets", str(bullets)]
     one = subprocess.run([cli] + common + ["--dump", str(tmp_path / "one")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          text=True, timeout=120)
     assert one.returncode == 0, one.stdout[-2000:]
@@ -106,6 +133,7 @@ def test_cpp_slab_system_matches_single_gpu(built, solver, tmp_path):
     den2 = np.concatenate([np.fromfile(tmp_path / f"two.rank{r}.density.f32", dtype=np.float32) for r in range(2)])
     assert pos2.shape == pos1.shape and sum(l["n_owned"] for l in lines) == pos1.shape[0], (pos1.shape, pos2.shape, lines)
     assert min(l["n_owned"] for l in lines) > 0.3 * pos1.shape[0], lines
+    assert bullets == 0 or lines[0]["strays_routed"] >= bullets, lines     # (with --bullets: fast particles, routed as strays)
     d, idx = cKDTree(pos2).query(pos1)
     assert np.unique(idx).size == idx.size, "the match between the two runs is not one-to-one"
     scale = max(1.0, float(np.abs(pos1).max()))

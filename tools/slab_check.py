@@ -22,6 +22,8 @@ ap.add_argument("--jitter", type=float, default=0.0)
 ap.add_argument("--rebalance", type=int, default=-1, help="re-balance the cuts every K steps (default: the driver's own setting)")
 ap.add_argument("--skew", type=int, default=0, help="start with the interior cuts this many planes off balance")
 ap.add_argument("--device-scene", action="store_true", help="ranks generate their columns / the boundary shell on the device (no host arrays)")
+ap.add_argument("--bullets", type=int, default=0, help="this many top-layer particles start with a velocity that carries them across "
+                "several cell planes per step (what a violent impact does): exercises the stray routing")
 a = ap.parse_args()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local = 0 if a.same_gpu else int(os.environ.get("LOCAL_RANK", rank))
@@ -38,16 +40,52 @@ if a.rebalance >= 0:
     os.environ["SPHK_SLAB_REBALANCE"] = str(a.rebalance)
 s = slabs.SlabSystem(sc_ranks, rank, world, torch.device("cuda", local), cut_skew=a.skew)
 cuts0 = list(s.cuts)
+
+
+def shoot(pos, vel):
+    """Gives the chosen top-layer lattice particles (found by position: the lattice survives step 0) their bullet velocity."""
+    if not a.bullets:
+        return 0
+    if sc.lattice is not None:
+        (nx, ny, nz), origin = sc.lattice
+    else:
+        lo, hi = sc.fluid.min(0), sc.fluid.max(0)
+        origin = tuple(float(x) for x in lo)
+        nx, ny, nz = (int(round(float(hi[k] - lo[k]) / 0.02)) + 1 for k in range(3))
+    idx = torch.round((pos - torch.tensor(origin, device=pos.device, dtype=pos.dtype)) / 0.02).to(torch.int64)
+    speed = 30.0 * 0.004 / float(sc.params.dt)             # ~3 planes per step
+    hit = 0
+    for b in range(a.bullets):
+        ix, iz = int((b + 0.5) * nx / a.bullets), nz // 2 + (b % 3) - 1
+        m = (idx[:, 0] == ix) & (idx[:, 1] == ny - 1) & (idx[:, 2] == iz)
+        v = torch.tensor([speed if b % 2 == 0 else -speed, 0.7 * speed, 0.0], device=pos.device, dtype=vel.dtype)
+        if a.solver == "pbd":       # PBD derives the velocity from the positions (PBDSolver.cu:56): displace the particle instead
+            pos[m] += float(sc.params.dt) * v
+        else:
+            vel[m] = v
+        hit += int(m.sum())
+    return hit
+
+
+if a.bullets:
+    assert a.jitter == 0.0, "--bullets finds its particles on the lattice"
+    s._refresh_ranges()
+    o0, o1 = s._ranges["own"]
+    shoot(s.fluid.pos[o0:o1], s.fluid.vel[o0:o1])
 states = [slabs.gather_state(s)]
+strays = 0
 for _ in range(a.steps):
     s.step()
+    strays += sum(s.stray_counts())
     states.append(slabs.gather_state(s))
 counts = [None] * world
 s._refresh_ranges()
 dist.all_gather_object(counts, (s.n_gl, s.n_own, s.n_gr, s.cuts))
 if rank == 0:
     ref = engine.SphkSystem(sc, device=torch.device("cuda", local))
-    out = {"world": world, "scene": a.scene, "solver": a.solver, "counts": counts, "steps": [], "cuts_initial": cuts0, "cuts_final": list(s.cuts),
+    if a.bullets:
+        assert shoot(ref.fluid.pos[:ref.fluid.n], ref.fluid.vel[:ref.fluid.n]) == a.bullets
+    out = {"strays_routed": strays, "world": world, "scene": a.scene, "solver": a.solver, "counts": counts, "steps": [], "cuts_initial": cuts0, "cuts_final": list(s.cuts),
            "rebalanced": s.rebalanced, "imbalance_at_last_rebalance": s.imbalance}
     ok = True
     for k, st in enumerate(states):
