@@ -122,7 +122,7 @@ SlabSPHSystem::SlabSPHSystem(std::shared_ptr<SPHParticles>& fluidParticles, std:
     const int nMine = static_cast<int>(mine.size());
     if (boot_.world > 1) {
         const char* e = std::getenv("SPHK_SLAB_STRAYS");
-        strayCap_ = e ? std::max(std::atoi(e), 0) : 1024;
+        strayCap_ = e ? std::max(std::atoi(e), 0) : 2048;
     }
     // (never above the global count: the solver's own buffers were sized with it at the reference call site, main.cpp:119-130)
     cap_ = std::min(static_cast<int>(std::max<double>(nMine, static_cast<double>(nGlobal_) / boot_.world) * 1.6) + 4096 + boot_.world * strayCap_, nGlobal_);

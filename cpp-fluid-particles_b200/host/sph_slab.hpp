@@ -72,7 +72,7 @@ private:
     std::unique_ptr<DArray<float>> altHist_;
     int* dBounds_ = nullptr;          // device: the 8 plane offsets gathered from csF_
     // strays (include/sphk.h): particles that crossed two or more planes in a step are routed to every rank
-    int strayCap_ = 0;                // per rank and step; SPHK_SLAB_STRAYS (default 1024, 0 = off)
+    int strayCap_ = 0;                // per rank and step; SPHK_SLAB_STRAYS (default 2048, 0 = off)
     float *strayBlock_ = nullptr, *strayGathered_ = nullptr;
     bool strayPending_ = false;
     void collectStrays();

@@ -301,7 +301,7 @@ class SlabSystem(SphkOps):
         n_total = scene.n_fluid
         # strays per rank and step that can be routed (SPHK_SLAB_STRAYS=0: off -- a particle that crosses two planes in a
         # step then stops the run with the ghost-plane mismatch error); world * stray_cap slots are appended to every search
-        self.stray_cap = int(os.environ.get("SPHK_SLAB_STRAYS", "1024")) if world > 1 else 0
+        self.stray_cap = int(os.environ.get("SPHK_SLAB_STRAYS", "2048")) if world > 1 else 0
         self._strays_pending = False
         self._n_scene_fluid = n_total
         if device_scene:
@@ -1195,8 +1195,13 @@ def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
         f1.record()
         torch.cuda.synchronize()
         e2e = (f0.elapsed_time(f1) / k2, h2d / k2, d2h / k2)
-    except Exception as exc:                               # the device-resident line above stays valid
-        print(f"[bench] rank {rank}: e2e leg failed: {exc}", file=sys.stderr, flush=True)
+    except RuntimeError as exc:
+        if "skipped:" not in str(exc):
+            # a rank that fails INSIDE the leg cannot tell the others (they wait for it in the next halo): take the job down
+            # at once instead of letting it sit on the GPUs until the watchdog fires
+            print(f"[bench] rank {rank}: e2e leg failed: {exc}", file=sys.stderr, flush=True)
+            raise
+        print(f"[bench] rank {rank}: e2e leg {exc}", file=sys.stderr, flush=True)   # agreed by all ranks: the line above stays valid
     t = torch.tensor([e2e[0] if e2e else -1.0, 0.0 if e2e else 1.0, e2e[1] if e2e else 0.0, e2e[2] if e2e else 0.0],
                      dtype=torch.float64, device=s.device)
     tmax = t.clone()
@@ -1207,6 +1212,8 @@ def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
     comm = s.comm_s / (args.steps + (0 if e2e is None else max(3, args.steps // 2)))
     assembly_ms = s.assembly_ms() if s.mg is not None else None
     bytes_sent, msgs = s.comm_stats()
+    strays = {"capacity_per_rank_and_step": s.stray_cap, "collected_per_rank_in_the_last_step": s.stray_counts(),
+              "note": "particles that crossed >= 2 cell planes in one step are routed to every rank (include/sphk.h, Strays)"}
     transport = {None: "torch.distributed P2P", 0: "NCCL send/recv (native)", 1: "peer-memory mailboxes (CUDA IPC over NVLink) + NCCL candidates"}[getattr(s, "transport", None) if s.mg is not None else None]
     s.close()
     dist.destroy_process_group()
@@ -1230,7 +1237,7 @@ def _bench_body(args, pkg, B, sc, n, rank, world, local, solver, scene_name):
                             "and downloads pos+vel+density into them (bytes summed over ranks)",
                      "timer": "CUDA events on the compute stream (copies are enqueued on it), max over ranks"}),
             "parity_checked": bool(parity and parity["parity_checked"]), "max_rel_err": (parity or {}).get("max_rel_err"), "parity": parity,
-            "gpu_launches": int(launches.item()), "halo": {"assembly_ms_per_step_device": assembly_ms,
+            "gpu_launches": int(launches.item()), "strays": strays, "halo": {"assembly_ms_per_step_device": assembly_ms,
                                                            "assembly_note": "candidate exchange + search of [ghosts|owned] + plane offsets (host read) + count "
                                                                             "exchange + list build, CUDA events on rank 0; the rest of the step is sweeps + one halo kernel each",
                                                            "host_wall_seconds_per_step_in_begin_step": comm,
