@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <string>
 #include <vector>
@@ -206,10 +207,14 @@ int main(int argc, char** argv) {
         }
         if (o.rank < 0) {
             int worstRc = 0;
-            for (const pid_t pid : kids) {
+            for (size_t left = kids.size(); left > 0; --left) {
                 int st = 0;
-                waitpid(pid, &st, 0);
+                const pid_t done = waitpid(-1, &st, 0);
+                if (done < 0) break;
                 const int rc = WIFEXITED(st) ? WEXITSTATUS(st) : 128;
+                if (rc != 0 && worstRc == 0)            // a rank that failed cannot be waited for by the others: end the job
+                    for (const pid_t pid : kids)
+                        if (pid != done) kill(pid, SIGKILL);
                 worstRc = rc > worstRc ? rc : worstRc;
             }
             for (const char* f : {"nccl_id"}) std::remove((o.rendezvous + "/" + f).c_str());
@@ -284,7 +289,14 @@ int main(int argc, char** argv) {
     float totalTime = 0.0f, worst = 0.0f;
     for (; frameId < o.frames;) {
         ++frameId;
-        const auto milliseconds = slab ? pSlab->step() : pSystem->step();
+        float milliseconds = 0.0f;
+        try {
+            milliseconds = slab ? pSlab->step() : pSystem->step();
+        } catch (const std::exception& e) {             // SlabSPHSystem::step: a broken decomposition contract ends the rank
+            std::fprintf(stderr, "sph_headless: %s\n", e.what());
+            std::fflush(nullptr);
+            _exit(4);
+        }
         if (slab && o.bullets > 0) straysRouted += pSlab->straysRouted();
         totalTime += milliseconds;
         worst = milliseconds > worst ? milliseconds : worst;

@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <stdexcept>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -63,7 +65,11 @@ std::vector<int> choose_cuts(const std::vector<long long>& countPerPlane, int wo
     return cuts;
 }
 
-__attribute__((unused)) const char* kNoDevice = "SlabSPHSystem: no usable CUDA device / engine (there is no CPU path)";
+// a rank that cannot keep the decomposition's contracts must not go on (its neighbours would compute with stale ghosts or wait for
+// it): the step throws, the caller ends the process, the launcher ends the job
+[[noreturn]] void fail(int rank, const std::string& what) {
+    throw std::runtime_error("SlabSPHSystem: rank " + std::to_string(rank) + ": " + what);
+}
 
 }  // namespace
 
@@ -332,7 +338,8 @@ void SlabSPHSystem::beginStep() {
     const int nl = L ? candFrom_[0] : 0, nr = R ? candFrom_[1] : 0;
     const int own0 = r_.own[0], nOwnPrev = r_.own[1] - r_.own[0];
     int nAll = nl + nOwnPrev + nr;
-    if (nAll + (strayPending_ ? boot_.world * strayCap_ : 0) > cap_) { printf("SlabSPHSystem: rank %d: capacity %d exceeded by %d local particles\n", boot_.rank, cap_, nAll); return; }
+    if (nAll + (strayPending_ ? boot_.world * strayCap_ : 0) > cap_)
+        fail(boot_.rank, "capacity " + std::to_string(cap_) + " exceeded by " + std::to_string(nAll) + " local particles");
     // carried arrays: pos, vel (+ the solver's history array), received straight into their slots of the assembled set
     float* live[3] = {reinterpret_cast<float*>(fluids_->getPosPtr()), reinterpret_cast<float*>(fluids_->getVelPtr()), hist};
     float* alt[3] = {reinterpret_cast<float*>(altPos_->addr()), reinterpret_cast<float*>(altVel_->addr()), altHist_->addr()};
@@ -370,12 +377,12 @@ void SlabSPHSystem::beginStep() {
         int fl[2] = {0, 0}, fr[2] = {0, 0};
         check(sphk_mg_exchange_ints(comm_, tl, tr, fl, fr, 2), "sphk_mg_exchange_ints");
         if ((L && fl[0] != nGhostL_) || (R && fr[0] != nGhostR_))
-            printf("SlabSPHSystem: rank %d: ghost planes %d/%d do not match the neighbours' boundary planes %d/%d (a particle moved "
-                   "more than one plane in a step?)\n", boot_.rank, nGhostL_, nGhostR_, fl[0], fr[0]);
+            fail(boot_.rank, "ghost planes " + std::to_string(nGhostL_) + "/" + std::to_string(nGhostR_) + " do not match the neighbours' boundary planes " +
+                                 std::to_string(fl[0]) + "/" + std::to_string(fr[0]) + " (more strays than SPHK_SLAB_STRAYS in one step?)");
         candFrom_[0] = fl[1]; candFrom_[1] = fr[1];
         int err = 0;
         check(sphk_mg_check(comm_, &err), "sphk_mg_check");
-        if (err) printf("SlabSPHSystem: rank %d: halo mailbox error bits %#x (see sphk_mg_check)\n", boot_.rank, err);
+        if (err) fail(boot_.rank, "halo mailbox error bits " + std::to_string(err) + " (see sphk_mg_check)");
     }
     haloRanges_[0] = r_.first[0]; haloRanges_[1] = nFirst; haloRanges_[2] = r_.last[0]; haloRanges_[3] = nLast;
     haloRanges_[4] = r_.ghostL[0]; haloRanges_[5] = nGhostL_; haloRanges_[6] = r_.ghostR[0]; haloRanges_[7] = nGhostR_;

@@ -36,7 +36,10 @@ public:
     SlabSPHSystem& operator=(const SlabSPHSystem&) = delete;
     ~SlabSPHSystem() noexcept;
 
-    float step();   // candidate exchange + neighbour search + solver step of this rank; milliseconds like SPHSystem::step
+    // candidate exchange + neighbour search + solver step of this rank; milliseconds like SPHSystem::step.  Collective: every rank
+    // calls it.  Throws std::runtime_error when this rank cannot keep the decomposition's contracts (capacity exceeded, ghost planes
+    // that do not match the neighbours', a halo that did not arrive): end the process then -- the other ranks wait for this one.
+    float step();
 
     bool ok() const { return ok_; }
     int size() const { return nOwn_; }                  // particles this rank owns
