@@ -316,6 +316,31 @@ def _native_worker(rank, world, port, steps, q, use_async=False):
             r = list((C.c_int * 8).from_address(val(ranges_ptr)))
             return self.sphk_mg_halo(mg, ctx, scene, what, ptr, width, r)
 
+        # ---- strays: the two kernels as their torch statements, the all-gather over gloo ----
+        def _views(self, k, ptrs, widths):
+            return [fview(ptrs[a], cap * widths[a]).reshape(cap, widths[a]) if widths[a] > 1 else fview(ptrs[a], cap) for a in range(val(k))]
+
+        def sphk_strays_collect(self, ctx, cs_ptr, a, cnt, k, ptrs, widths, block_ptr, capacity):
+            a, cnt, capacity, pc = val(a), val(cnt), val(capacity), CY * CZ
+            arrays = self._views(k, ptrs, widths)
+            cs = np.ctypeslib.as_array((C.c_int * ((w + 2) * pc + 1)).from_address(val(cs_ptr)))
+            offs = cs[::pc][:w + 3]
+            plane_sorted = np.searchsorted(offs, np.arange(a, a + cnt), side="right") - 1
+            plane_now = np.floor(arrays[0][a:a + cnt, 0].numpy()).astype(np.int64) - (x0 - 1)
+            block = slabs.collect_strays_host(arrays, (a, a + cnt), plane_sorted, plane_now, capacity)
+            fview(val(block_ptr), block.numel()).copy_(block)
+            return 0
+
+        def sphk_mg_strays_route(self, mg, ctx, block_ptr, gathered_ptr, capacity, k, ptrs, widths, dst_begin):
+            capacity = val(capacity)
+            nf = slabs.stray_block_floats(capacity, [widths[a] for a in range(val(k))])
+            parts = [torch.zeros(nf) for _ in range(world)]
+            dist.all_gather(parts, fview(val(block_ptr), nf).clone())
+            gathered = fview(val(gathered_ptr), world * nf)
+            gathered.copy_(torch.cat(parts))
+            slabs.append_strays_host(gathered, world, capacity, self._views(k, ptrs, widths), val(dst_begin))
+            return 0
+
     class Fluid:
         pass
 
@@ -331,7 +356,9 @@ def _native_worker(rank, world, port, steps, q, use_async=False):
         _search_all = slabs.SlabSystem._search_all
         _halo = slabs.SlabSystem._halo
         _route_strays = slabs.SlabSystem._route_strays
-        stray_cap, _strays_pending = 0, False      # (the routing has its own gloo test above, on the torch statements of the kernels)
+        _collect_strays = slabs.SlabSystem._collect_strays
+        _array_args = slabs.SlabSystem._array_args
+        stray_cap, _strays_pending = 64, False
 
         def _s(self):
             return None
@@ -360,7 +387,7 @@ def _native_worker(rank, world, port, steps, q, use_async=False):
     s.async_assembly, s.transport, s._async_pending, s._step_async = use_async, 1, False, False
     s._dev24, s._pin24, s._pin_misc = torch.zeros(24, dtype=torch.int32), torch.zeros(24, dtype=torch.int32), torch.zeros(8, dtype=torch.int32)
     s._async_event = type("Ev", (), {"record": lambda self: None, "synchronize": lambda self: None})()
-    used_async = 0
+    used_async = strays = 0
     mine = (plane >= x0) & (plane < x1)
     s.n_own = int(mine.sum())
     s.fluid.pos[:s.n_own] = torch.from_numpy(pos[mine])
@@ -370,6 +397,8 @@ def _native_worker(rank, world, port, steps, q, use_async=False):
         if step > 0:                      # every rank moves the GLOBAL set identically (< 1 plane), its own particles accordingly
             dx = rng.uniform(-0.45, 0.45, (n, 3)).astype(np.float32)
             dx[:, 1:] *= 0.2
+            fast = rng.integers(0, 100, n) == 0                       # ... except 1 %: up to four planes (strays)
+            dx[fast, 0] = rng.uniform(-4.0, 4.0, int(fast.sum())).astype(np.float32)
             pos = pos + dx
             pos[:, 0] = np.clip(pos[:, 0], 0.05, CX - 0.05)
             pos[:, 1] = np.clip(pos[:, 1], 0.01, CY - 0.01); pos[:, 2] = np.clip(pos[:, 2], 0.01, CZ - 0.01)
@@ -377,6 +406,8 @@ def _native_worker(rank, world, port, steps, q, use_async=False):
             a0, a1 = s._ranges["own"]
             ids = s.fluid.vel[a0:a1, 0].numpy().astype(np.int64)
             s.fluid.pos[a0:a1] = torch.from_numpy(pos[ids])
+            s._collect_strays()               # what SlabSystem.step does before begin_step
+            strays += int(s._stray_block[:1].view(torch.int32)[0])
         s.begin_step()
         used_async += int(s._step_async)
         if step % 2 == 0:
@@ -408,9 +439,9 @@ def _native_worker(rank, world, port, steps, q, use_async=False):
         ok &= bool(np.array_equal(g3[:h1].numpy(), pos[ids] * np.float32(2.0)))
     ok &= used_async == (steps - 1 if use_async else 0)     # the first step sizes itself synchronously, every later one is host-free
     allok = [None] * world
-    dist.all_gather_object(allok, bool(ok))
+    dist.all_gather_object(allok, (bool(ok), strays))
     if rank == 0:
-        q.put(all(allok))
+        q.put(all(o for o, _ in allok) and sum(c for _, c in allok) > 20)      # (and the stray routing was exercised)
     dist.destroy_process_group()
 
 
