@@ -82,6 +82,7 @@ struct sphk_ctx {
     const int* listRangeDev = nullptr;
     int kmax = 96;
     bool useList = true;
+    int patch = 0;                   // SPHK_OPT_PATCH (experiment): list sweeps map a block onto a y x z patch of cells
     bool stagedBuild = true;         // build the list from candidate windows staged in shared memory by bulk copies (default);
                                      // false: candidates read from global memory (k_build_list)
     bool simpleBuild = false;        // build the list with the generic cell walk (test reference of k_build_list)
@@ -118,6 +119,7 @@ struct DevScene {
                                      // contributes exactly 0 to every particle (group lists cannot pad with "self")
     int iBegin, iEnd;                // sweeps compute particles [iBegin, iEnd)
     const int* rangeDev;             // non-null: ... intersected with the device-resident range {begin, count}
+    int patch;                       // > 0: the warps of a block take their 32-particle chunks from 4 runs `patch` chunks apart
     int3 cs, org;
     float cellLength;
     float r2list;                    // candidate cut-off of the cell walk: r2cut, or (R + skin)^2 when building a skin list

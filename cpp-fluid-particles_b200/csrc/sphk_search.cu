@@ -244,6 +244,7 @@ extern "C" int sphk_set_option(sphk_ctx* c, int option, int value) {
         }
         return SPHK_OK;
     case SPHK_OPT_SIMPLE_LIST_BUILD: c->simpleBuild = value != 0; c->listEpoch = ~0ull; return SPHK_OK;
+    case SPHK_OPT_PATCH: if (value < 0) return SPHK_ERR_INVALID; c->patch = value; return SPHK_OK;
     case SPHK_OPT_STAGED_LIST_BUILD: c->stagedBuild = value != 0; c->listEpoch = ~0ull; return SPHK_OK;
     case SPHK_OPT_LIST_SKIN:
         if (value < 0 || value > 1000) return SPHK_ERR_INVALID;

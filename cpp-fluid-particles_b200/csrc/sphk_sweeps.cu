@@ -438,7 +438,13 @@ __device__ __forceinline__ void sweep_list_particle(const DevScene& s, const Op&
 template <class Op>
 __global__ void __launch_bounds__(SPHK_BLOCK) k_sweep_list(const DevScene s, const Op op) {
     if (s.pred && *s.pred == 0) return;
-    const int i = s.iBegin + blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    int t = blockIdx.x * SPHK_BLOCK + threadIdx.x;
+    if (s.patch > 0) {               // groups of 4 runs of `patch` chunks; block bb of a group: chunk bb of each run, one per warp
+        static_assert(SPHK_BLOCK == 128, "four warps per block");
+        const int chunk = t >> 5, per = 4 * s.patch, g = chunk / per, r = chunk - g * per;
+        t = ((g * per + (r & 3) * s.patch + (r >> 2)) << 5) | (t & 31);
+    }
+    const int i = s.iBegin + t;
     if (!in_range(s, i)) return;
     sweep_list_particle(s, op, i);
 }
@@ -982,6 +988,7 @@ static DevScene dev_scene(const sphk_ctx* c, const sphk_scene* s) {
     d.iBegin = c->actCount < 0 ? 0 : c->actBegin;
     d.iEnd = c->actCount < 0 ? c->nF : c->actBegin + c->actCount;
     d.rangeDev = c->rangeDev;
+    d.patch = c->patch;
     if (c->rangeDev) { d.iBegin = 0; d.iEnd = c->nF; }      // launched over everything, cut on the device
     d.k = kernel_constants(s->radius);
     d.r2list = d.k.r2cut;
@@ -1060,7 +1067,11 @@ template <class Op> static int run_sweep(sphk_ctx* c, const sphk_scene* s, const
             const int tiles = (d.iEnd + SPHK_BLOCK - 1) / SPHK_BLOCK - d.iBegin / SPHK_BLOCK;
             k_sweep_tile<Op><<<tiles, SPHK_BLOCK, smem, c->stream>>>(d, op);
         }
-        else k_sweep_list<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
+        else {
+            int blocks = sphk_blocks(d.iEnd - d.iBegin);
+            if (d.patch > 0) blocks = (blocks + d.patch - 1) / d.patch * d.patch;      // whole groups (4 * patch chunks = patch blocks)
+            k_sweep_list<Op><<<blocks, SPHK_BLOCK, 0, c->stream>>>(d, op);
+        }
     } else {
         k_sweep_cells<Op><<<sphk_blocks(d.iEnd - d.iBegin), SPHK_BLOCK, 0, c->stream>>>(d, op);
     }

@@ -82,6 +82,10 @@ enum {
                                     to the cell walk individually.  default 96 */
     SPHK_OPT_STAGED_LIST_BUILD = 10, /* 1 (default): the list builder stages each tile's 9 + 9 candidate windows in shared memory
                                     (cp.async.bulk + mbarrier) and tests candidates from there; 0: candidates read from global memory */
+    SPHK_OPT_PATCH = 11,         /* experiment (default 0 = off): S > 0 makes the 4 warps of a list-sweep block take their
+                                    32-particle chunks from 4 runs that lie S chunks apart in the sorted order instead of 4
+                                    consecutive chunks -- with S = chunks per cell column, a block covers 4 adjacent columns x 4 cells
+                                    in z, a smaller neighbour footprint per block (L1 reuse).  Results are unchanged. */
     SPHK_OPT_SIMPLE_LIST_BUILD = 6, /* 1: build the list with the generic cell walk (reference for the tuned builder) */
     SPHK_OPT_LIST_SKIN = 5,      /* neighbour-list skin in 1/1000 of the radius (default 0).  With a skin the list
                                     stays valid while sphk_pbd_delta_pos_apply moves particles by less than skin/2
