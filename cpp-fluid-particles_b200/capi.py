@@ -36,7 +36,7 @@ SPH_APP_FUNCTIONS = [
     "sph_app_submit", "sph_app_wait", "sph_app_dfsph_iterations", "sph_app_set_option",
 ]
 
-OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_LIST_SKIN, OPT_SIMPLE_LIST_BUILD, OPT_TILE, OPT_STAGED_LIST_BUILD = 1, 2, 5, 6, 9, 10
+OPT_NEIGHBOR_LIST, OPT_LIST_CAPACITY, OPT_LIST_SKIN, OPT_SIMPLE_LIST_BUILD, OPT_TILE, OPT_STAGED_LIST_BUILD, OPT_PATCH = 1, 2, 5, 6, 9, 10, 11
 
 
 class SphkGrid(C.Structure):

@@ -289,6 +289,24 @@ def test_tile_lists_reproduce_global_lists(pkg, built, O, solver):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("stride", [5, 16])
+def test_patch_mapped_sweep_blocks_change_nothing(pkg, built, O, stride):
+    """SPHK_OPT_PATCH (experiment): the warps of a list-sweep block take their 32-particle chunks from four runs `stride`
+    chunks apart instead of four consecutive ones.  Only the thread -> particle assignment changes (a bijection, also over
+    the ragged last group): every particle is computed exactly as before, bit for bit."""
+    _torch()
+    from cpp_fluid_particles_b200 import capi, engine
+    sc = pkg.scene.benchmark_scene("config0", "dfsph")
+    a, b = engine.SphkSystem(sc, step0=False), engine.SphkSystem(sc, step0=False)
+    b.set_option(capi.OPT_PATCH, stride)
+    for k in range(3):
+        a.step(); b.step()
+        sa, sb = a.state(), b.state()
+        for f in ("pos", "vel", "density", "pressure"):
+            assert np.array_equal(sa[f], sb[f]), (f, k)
+    a.close(); b.close()
+
+
 def test_pbd_skin_list_with_fast_movers(pkg, built, O):
     """PBD moves particles inside a step (Q7); its neighbour list carries a skin and stays valid for particles that moved
     less than skin/2.  A strongly jittered block makes the first projections move many particles further than that: they
