@@ -212,10 +212,11 @@ int main(int argc, char** argv) {
                 const pid_t done = waitpid(-1, &st, 0);
                 if (done < 0) break;
                 const int rc = WIFEXITED(st) ? WEXITSTATUS(st) : 128;
-                if (rc != 0 && worstRc == 0)            // a rank that failed cannot be waited for by the others: end the job
+                if (rc != 0 && worstRc == 0) {          // a rank that failed cannot be waited for by the others: end the job
+                    worstRc = rc;                       // (and report ITS exit code, not that of the ranks killed here)
                     for (const pid_t pid : kids)
                         if (pid != done) kill(pid, SIGKILL);
-                worstRc = rc > worstRc ? rc : worstRc;
+                }
             }
             for (const char* f : {"nccl_id"}) std::remove((o.rendezvous + "/" + f).c_str());
             for (int r = 0; r < o.ranks; ++r)
