@@ -87,6 +87,14 @@ def test_mg_entry_points_validate_arguments(pkg, built):
     assert L.sphk_mg_exchange_slices(None, 1, None, None, None, None, None, None, None) == -1
     assert L.sphk_mg_set_transport(None, 1) == -1
     assert L.sphk_mg_check(None, None) == -1
+    # strays: block size arithmetic {4 header floats + capacity * sum(widths)} and argument validation
+    w3 = (C.c_int * 3)(3, 3, 1)
+    assert L.sphk_strays_block_floats(2048, 3, w3) == 4 + 2048 * 7
+    assert L.sphk_strays_block_floats(8, 5, w3) == -1 and L.sphk_strays_block_floats(-1, 3, w3) == -1
+    assert L.sphk_strays_collect(None, None, 0, 0, 3, None, w3, None, 8) == -1
+    assert L.sphk_strays_append(None, None, 2, 8, 3, None, w3, 0) == -1
+    assert L.sphk_mg_strays_route(None, None, None, None, 8, 3, None, w3, 0) == -1
+    assert L.sphk_strays_counts(None, None, 2, 8, 3, w3, None) == -1
     L.sphk_mg_destroy(None)                                                             # no-op
     assert b"multi-GPU" in L.sphk_error_string(-6)
     if not torch.cuda.is_available():
